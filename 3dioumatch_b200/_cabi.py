@@ -1,0 +1,73 @@
+"""ctypes binding of libb200pc.so (include/b200_pointnet2.h, include/b200_iou3d.h).
+
+There is no CPU or PyTorch fallback: if the library is missing, every operator raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200pc.so")
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+class MlpLayer(ctypes.Structure):
+    """b200_mlp_layer"""
+    _fields_ = [("cin", c_int), ("cout", c_int), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/*.h
+PROTOTYPES = {
+    "b200_abi_version": (c_int, []),
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_launch_count": (ctypes.c_ulonglong, []),
+    "b200pn2_furthest_point_sampling": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_gather_points": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_gather_points_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_ball_query": (c_int, [c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_group_points": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_group_points_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_three_nn": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200pn2_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p]),
+    "b200pn2_sa_forward_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "b200pn2_sa_forward": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200iou_boxes_overlap_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200iou_boxes_iou_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200iou_boxes_iou3d": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200iou_boxes_iou3d_batched": (c_int, [c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200iou_nms_device": (c_int, [c_int, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200iou_nms": (c_int, [c_int, c_void_p, c_float, c_int, c_void_p, ctypes.POINTER(c_int), c_void_p]),
+    "b200iou_boxes_iou_bev_cpu": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libb200pc.so and bind every prototype.  Raises RuntimeError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "3dioumatch_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C 3dioumatch_b200/csrc`; there is no CPU/PyTorch fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError here == header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib().b200_launch_count())

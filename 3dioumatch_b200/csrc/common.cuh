@@ -1,0 +1,71 @@
+// common.cuh -- shared host/device helpers of libb200pc.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+namespace b200 {
+
+// ---- error reporting (C ABI: int status + b200_last_error()) -------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+#define B200_CHECK_ARG(cond, ...)  \
+  do {                             \
+    if (!(cond)) {                 \
+      b200::set_error(__VA_ARGS__); \
+      return 1;                    \
+    }                              \
+  } while (0)
+
+#define B200_CUDA_OK(expr)                                                                    \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      b200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 2;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define B200_LAUNCH_OK(name)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      b200::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 3;                                                                                \
+    }                                                                                          \
+    b200::count_launch();                                                                      \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- the reference's squared-distance rounding sequence -------------------------------------
+// nvcc contracts (a*a + b*b + c*c) of the reference kernels (ball_query_gpu.cu:36-37,
+// sampling_gpu.cu:105,108-109, interpolate_gpu.cu:38) for sm_100a into
+//     fma(c,c, fma(a,a, mul(b,b)))
+// Index parity is bit-exact, so the sequence is pinned with intrinsics the compiler may
+// not re-associate or re-contract.
+__device__ __forceinline__ float sq3(float a, float b, float c) {
+  float t = __fmul_rn(b, b);
+  t = __fmaf_rn(a, a, t);
+  return __fmaf_rn(c, c, t);
+}
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  return sq3(__fsub_rn(ax, bx), __fsub_rn(ay, by), __fsub_rn(az, bz));
+}
+
+}  // namespace b200

@@ -1,0 +1,265 @@
+// point_ops.cu -- gather / group / three_nn / three_interpolate (+ gradients) for sm_100a.
+//
+// The reference launches B thread blocks for every one of these (sampling_gpu.cu:27-33, group_points_gpu.cu:35-43,
+// interpolate_gpu.cu:66-73,108-116): 8 of 148 SMs at B=8.  They are pure data movement (HBM/L2-bound), so the
+// B200 versions are laid out for coalescing and a grid that fills the machine:
+//   * index / weight tensors are read once per output row and reused across a chunk of channels,
+//   * the innermost (contiguous) output dimension maps to threadIdx.x,
+//   * grids are sized from the element count, not from B.
+#include "../../include/b200_pointnet2.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int PO_THREADS = 256;
+constexpr int PO_CCHUNK = 8;  // channels handled by one thread (index reuse)
+
+// out[b,c,j] = points[b,c,idx[b,j]]            (sampling_gpu.cu:13-25)
+__global__ void __launch_bounds__(PO_THREADS)
+gather_points_kernel(int C, int N, int m, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                     float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (j >= m) return;
+  const int a = idx[(size_t)b * m + j];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c) out[((size_t)b * C + c) * m + j] = points[((size_t)b * C + c) * N + a];
+}
+
+// grad_points[b,c,idx[b,j]] += grad_out[b,c,j]  (sampling_gpu.cu:39-52)
+__global__ void __launch_bounds__(PO_THREADS)
+gather_points_grad_kernel(int C, int N, int m, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                          float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (j >= m) return;
+  const int a = idx[(size_t)b * m + j];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c)
+    atomicAdd(grad_points + ((size_t)b * C + c) * N + a, grad_out[((size_t)b * C + c) * m + j]);
+}
+
+// out[b,c,j,k] = points[b,c,idx[b,j,k]]        (group_points_gpu.cu:13-32); e = j*ns + k is contiguous
+__global__ void __launch_bounds__(PO_THREADS)
+group_points_kernel(int C, int N, int MK, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                    float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int e = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (e >= MK) return;
+  const int a = idx[(size_t)b * MK + e];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c) out[((size_t)b * C + c) * MK + e] = points[((size_t)b * C + c) * N + a];
+}
+
+// grad_points[b,c,idx[b,j,k]] += grad_out[b,c,j,k]   (group_points_gpu.cu:48-68)
+__global__ void __launch_bounds__(PO_THREADS)
+group_points_grad_kernel(int C, int N, int MK, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                         float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int e = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (e >= MK) return;
+  const int a = idx[(size_t)b * MK + e];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c)
+    atomicAdd(grad_points + ((size_t)b * C + c) * N + a, grad_out[((size_t)b * C + c) * MK + e]);
+}
+
+// three_nn (interpolate_gpu.cu:14-64): one thread per unknown point, the known set streamed through a
+// shared-memory tile shared by the whole CTA.  The reference keeps `double` bests initialised to 1e40 and
+// compares the fp32 distance with strict `<`; fp32 bests initialised to +inf select exactly the same entries
+// (an fp32 distance is never >= 1e40 unless it is +inf/NaN, which never pass `<` in either form) and
+// (float)1e40 == +inf is what the reference stores for unfilled slots.
+constexpr int NN_TILE = 1024;
+__global__ void __launch_bounds__(PO_THREADS)
+three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                float *__restrict__ dist2, int32_t *__restrict__ idx) {
+  __shared__ float s_known[NN_TILE * 3];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * PO_THREADS + threadIdx.x;
+  const bool active = j < n;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (active) {
+    const float *u = unknown + ((size_t)b * n + j) * 3;
+    ux = u[0]; uy = u[1]; uz = u[2];
+  }
+  const float inf = __int_as_float(0x7f800000);
+  float best1 = inf, best2 = inf, best3 = inf;
+  int besti1 = 0, besti2 = 0, besti3 = 0;
+  const float *kn = known + (size_t)b * m * 3;
+  for (int t0 = 0; t0 < m; t0 += NN_TILE) {
+    const int tn = min(NN_TILE, m - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += PO_THREADS) s_known[i] = kn[(size_t)t0 * 3 + i];
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int k = 0; k < tn; ++k) {
+        const float d = sqdist3(ux, uy, uz, s_known[k * 3], s_known[k * 3 + 1], s_known[k * 3 + 2]);  // :38 (u - x)
+        if (d < best3) {  // cheap reject; the cascade below is the reference's (:39-54)
+          if (d < best1) {
+            best3 = best2; besti3 = besti2;
+            best2 = best1; besti2 = besti1;
+            best1 = d; besti1 = t0 + k;
+          } else if (d < best2) {
+            best3 = best2; besti3 = besti2;
+            best2 = d; besti2 = t0 + k;
+          } else {
+            best3 = d; besti3 = t0 + k;
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    float *dd = dist2 + ((size_t)b * n + j) * 3;
+    int32_t *ii = idx + ((size_t)b * n + j) * 3;
+    dd[0] = best1; dd[1] = best2; dd[2] = best3;
+    ii[0] = besti1; ii[1] = besti2; ii[2] = besti3;
+  }
+}
+
+// out[b,c,j] = fma(p3,w3, fma(p1,w1, p2*w2))    (interpolate_gpu.cu:77-106 and its sm_100a contraction)
+__global__ void __launch_bounds__(PO_THREADS)
+three_interpolate_kernel(int C, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                         const float *__restrict__ weight, float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (j >= n) return;
+  const float *w = weight + ((size_t)b * n + j) * 3;
+  const int32_t *ii = idx + ((size_t)b * n + j) * 3;
+  const float w1 = w[0], w2 = w[1], w3 = w[2];
+  const int i1 = ii[0], i2 = ii[1], i3 = ii[2];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c) {
+    const float *p = points + ((size_t)b * C + c) * m;
+    float t = __fmul_rn(p[i2], w2);
+    t = __fmaf_rn(p[i1], w1, t);
+    out[((size_t)b * C + c) * n + j] = __fmaf_rn(p[i3], w3, t);
+  }
+}
+
+// grad_points[b,c,idx[b,j,t]] += grad_out[b,c,j] * weight[b,j,t]   (interpolate_gpu.cu:121-148)
+__global__ void __launch_bounds__(PO_THREADS)
+three_interpolate_grad_kernel(int C, int n, int m, const float *__restrict__ grad_out,
+                              const int32_t *__restrict__ idx, const float *__restrict__ weight,
+                              float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * PO_THREADS + threadIdx.x;
+  if (j >= n) return;
+  const float *w = weight + ((size_t)b * n + j) * 3;
+  const int32_t *ii = idx + ((size_t)b * n + j) * 3;
+  const float w1 = w[0], w2 = w[1], w3 = w[2];
+  const int i1 = ii[0], i2 = ii[1], i3 = ii[2];
+  const int c_begin = blockIdx.y * PO_CCHUNK, c_end = min(C, c_begin + PO_CCHUNK);
+  for (int c = c_begin; c < c_end; ++c) {
+    const float go = grad_out[((size_t)b * C + c) * n + j];
+    float *g = grad_points + ((size_t)b * C + c) * m;
+    atomicAdd(g + i1, go * w1);
+    atomicAdd(g + i2, go * w2);
+    atomicAdd(g + i3, go * w3);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_DIMS_OK(name, B, ...)                                                          \
+  do {                                                                                      \
+    const long long _d[] = {__VA_ARGS__};                                                   \
+    for (unsigned _i = 0; _i < sizeof(_d) / sizeof(_d[0]); ++_i)                            \
+      B200_CHECK_ARG(_d[_i] >= 0, "%s: negative dimension", name);                          \
+    B200_CHECK_ARG((B) <= 65535, "%s: B=%d exceeds grid.z", name, (int)(B));                \
+  } while (0)
+
+extern "C" int b200pn2_gather_points(int B, int C, int N, int m, const float *points, const int32_t *idx, float *out,
+                                     b200_stream_t s) {
+  B200_DIMS_OK("gather_points", B, B, C, N, m);
+  if (B == 0 || C == 0 || m == 0) return 0;
+  B200_CHECK_ARG(points && idx && out, "gather_points: null pointer");
+  dim3 grid(ceil_div(m, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  gather_points_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, N, m, points, idx, out);
+  B200_LAUNCH_OK("gather_points_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_gather_points_grad(int B, int C, int N, int m, const float *grad_out, const int32_t *idx,
+                                          float *grad_points, b200_stream_t s) {
+  B200_DIMS_OK("gather_points_grad", B, B, C, N, m);
+  if (B == 0 || C == 0 || N == 0) return 0;
+  B200_CHECK_ARG(grad_points, "gather_points_grad: null pointer");
+  B200_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * N, (cudaStream_t)s));
+  if (m == 0) return 0;
+  B200_CHECK_ARG(grad_out && idx, "gather_points_grad: null pointer");
+  dim3 grid(ceil_div(m, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  gather_points_grad_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, N, m, grad_out, idx, grad_points);
+  B200_LAUNCH_OK("gather_points_grad_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_group_points(int B, int C, int N, int M, int ns, const float *points, const int32_t *idx,
+                                    float *out, b200_stream_t s) {
+  B200_DIMS_OK("group_points", B, B, C, N, M, ns);
+  if (B == 0 || C == 0 || M == 0 || ns == 0) return 0;
+  B200_CHECK_ARG(points && idx && out, "group_points: null pointer");
+  const long long MK = (long long)M * ns;
+  B200_CHECK_ARG(MK < (1ll << 31), "group_points: M*nsample too large");
+  dim3 grid(ceil_div((int)MK, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  group_points_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, N, (int)MK, points, idx, out);
+  B200_LAUNCH_OK("group_points_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_group_points_grad(int B, int C, int N, int M, int ns, const float *grad_out,
+                                         const int32_t *idx, float *grad_points, b200_stream_t s) {
+  B200_DIMS_OK("group_points_grad", B, B, C, N, M, ns);
+  if (B == 0 || C == 0 || N == 0) return 0;
+  B200_CHECK_ARG(grad_points, "group_points_grad: null pointer");
+  B200_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * N, (cudaStream_t)s));
+  if (M == 0 || ns == 0) return 0;
+  B200_CHECK_ARG(grad_out && idx, "group_points_grad: null pointer");
+  const long long MK = (long long)M * ns;
+  B200_CHECK_ARG(MK < (1ll << 31), "group_points_grad: M*nsample too large");
+  dim3 grid(ceil_div((int)MK, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  group_points_grad_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, N, (int)MK, grad_out, idx, grad_points);
+  B200_LAUNCH_OK("group_points_grad_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_three_nn(int B, int n, int m, const float *unknown, const float *known, float *dist2,
+                                int32_t *idx, b200_stream_t s) {
+  B200_DIMS_OK("three_nn", 0, B, n, m);
+  B200_CHECK_ARG(B <= 65535, "three_nn: B=%d exceeds grid.y", B);
+  if (B == 0 || n == 0) return 0;
+  B200_CHECK_ARG(unknown && dist2 && idx && (known || m == 0), "three_nn: null pointer");
+  dim3 grid(ceil_div(n, PO_THREADS), B);
+  three_nn_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(n, m, unknown, known, dist2, idx);
+  B200_LAUNCH_OK("three_nn_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_three_interpolate(int B, int C, int m, int n, const float *points, const int32_t *idx,
+                                         const float *weight, float *out, b200_stream_t s) {
+  B200_DIMS_OK("three_interpolate", B, B, C, m, n);
+  if (B == 0 || C == 0 || n == 0) return 0;
+  B200_CHECK_ARG(points && idx && weight && out, "three_interpolate: null pointer");
+  dim3 grid(ceil_div(n, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  three_interpolate_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, m, n, points, idx, weight, out);
+  B200_LAUNCH_OK("three_interpolate_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_three_interpolate_grad(int B, int C, int n, int m, const float *grad_out, const int32_t *idx,
+                                              const float *weight, float *grad_points, b200_stream_t s) {
+  B200_DIMS_OK("three_interpolate_grad", B, B, C, m, n);
+  if (B == 0 || C == 0 || m == 0) return 0;
+  B200_CHECK_ARG(grad_points, "three_interpolate_grad: null pointer");
+  B200_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)B * C * m, (cudaStream_t)s));
+  if (n == 0) return 0;
+  B200_CHECK_ARG(grad_out && idx && weight, "three_interpolate_grad: null pointer");
+  dim3 grid(ceil_div(n, PO_THREADS), ceil_div(C, PO_CCHUNK), B);
+  three_interpolate_grad_kernel<<<grid, PO_THREADS, 0, (cudaStream_t)s>>>(C, n, m, grad_out, idx, weight,
+                                                                          grad_points);
+  B200_LAUNCH_OK("three_interpolate_grad_kernel");
+  return 0;
+}

@@ -1,0 +1,201 @@
+"""Drop-in for the reference's native module `pointnet2._ext`
+(pointnet2/_ext_src/src/bindings.cpp:11-24): same nine functions, same argument order, dtypes, shapes and
+error behaviour (RuntimeError for non-contiguous / wrong dtype / CPU tensors, utils.h:10-30), implemented
+by the hand-written sm_100a kernels of libb200pc.so through its C ABI.  Outputs are allocated by the callee
+on the input's device; launches go to the current torch stream.  No CPU path exists ("CPU not supported",
+as in the reference)."""
+import ctypes
+
+import torch
+
+from _b200_bridge import cabi, stream_ptr
+
+_L = cabi.lib
+
+
+def _chk(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _contig(t, name):
+    _chk(t.is_contiguous(), "%s must be a contiguous tensor" % name)
+
+
+def _is_float(t, name):
+    _chk(t.dtype == torch.float32, "%s must be a float tensor" % name)
+
+
+def _is_int(t, name):
+    _chk(t.dtype == torch.int32, "%s must be an int tensor" % name)
+
+
+def _cuda(t, name):
+    _chk(t.is_cuda, "CPU not supported" if name is None else "%s must be a CUDA tensor" % name)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def furthest_point_sampling(points, nsamples):
+    """(B,N,3) f32 -> (B,nsamples) int32   [sampling.cpp:70-91]"""
+    _contig(points, "points"); _is_float(points, "points"); _cuda(points, None)
+    B, N = points.size(0), points.size(1)
+    out = torch.empty((B, int(nsamples)), dtype=torch.int32, device=points.device)
+    if B == 0 or nsamples == 0:
+        return out
+    with torch.cuda.device(points.device):
+        cabi.check(_L().b200pn2_furthest_point_sampling(B, N, int(nsamples), _p(points), _p(out), None, stream_ptr()),
+                   "furthest_point_sampling")
+    return out
+
+
+def gather_points(points, idx):
+    """(B,C,N) f32, (B,m) i32 -> (B,C,m)   [sampling.cpp:20-44]"""
+    _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")
+    _cuda(points, None); _cuda(idx, "idx")
+    B, C, N = points.shape
+    m = idx.size(1)
+    out = torch.empty((B, C, m), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        cabi.check(_L().b200pn2_gather_points(B, C, N, m, _p(points), _p(idx), _p(out), stream_ptr()), "gather_points")
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    """(B,C,m) f32, (B,m) i32, n -> (B,C,n)   [sampling.cpp:46-69]"""
+    _contig(grad_out, "grad_out"); _contig(idx, "idx"); _is_float(grad_out, "grad_out"); _is_int(idx, "idx")
+    _cuda(grad_out, None); _cuda(idx, "idx")
+    B, C, m = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        cabi.check(_L().b200pn2_gather_points_grad(B, C, int(n), m, _p(grad_out), _p(idx), _p(out), stream_ptr()),
+                   "gather_points_grad")
+    return out
+
+
+def three_nn(unknowns, knows):
+    """(B,n,3), (B,m,3) -> [dist2 (B,n,3) f32, idx (B,n,3) i32]   [interpolate.cpp:19-45]"""
+    _contig(unknowns, "unknowns"); _contig(knows, "knows"); _is_float(unknowns, "unknowns"); _is_float(knows, "knows")
+    _cuda(unknowns, None); _cuda(knows, "knows")
+    B, n = unknowns.size(0), unknowns.size(1)
+    m = knows.size(1)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    with torch.cuda.device(unknowns.device):
+        cabi.check(_L().b200pn2_three_nn(B, n, m, _p(unknowns), _p(knows), _p(dist2), _p(idx), stream_ptr()), "three_nn")
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    """(B,c,m) f32, (B,n,3) i32, (B,n,3) f32 -> (B,c,n)   [interpolate.cpp:47-74]"""
+    for t, nm in ((points, "points"), (idx, "idx"), (weight, "weight")):
+        _contig(t, nm)
+    _is_float(points, "points"); _is_int(idx, "idx"); _is_float(weight, "weight")
+    _cuda(points, None); _cuda(idx, "idx"); _cuda(weight, "weight")
+    B, C, m = points.shape
+    n = idx.size(1)
+    out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        cabi.check(_L().b200pn2_three_interpolate(B, C, m, n, _p(points), _p(idx), _p(weight), _p(out), stream_ptr()),
+                   "three_interpolate")
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """(B,c,n) f32, idx, weight, m -> (B,c,m): the true scatter-add gradient (interpolate_gpu.cu:121-148).
+    The reference's host wrapper launches the forward kernel here by mistake (interpolate.cpp:95)."""
+    for t, nm in ((grad_out, "grad_out"), (idx, "idx"), (weight, "weight")):
+        _contig(t, nm)
+    _is_float(grad_out, "grad_out"); _is_int(idx, "idx"); _is_float(weight, "weight")
+    _cuda(grad_out, None); _cuda(idx, "idx"); _cuda(weight, "weight")
+    B, C, n = grad_out.shape
+    out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        cabi.check(_L().b200pn2_three_interpolate_grad(B, C, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(out),
+                                                       stream_ptr()), "three_interpolate_grad")
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """(B,M,3), (B,N,3), radius, nsample -> (B,M,nsample) i32   [ball_query.cpp:13-37]"""
+    _contig(new_xyz, "new_xyz"); _contig(xyz, "xyz"); _is_float(new_xyz, "new_xyz"); _is_float(xyz, "xyz")
+    _cuda(new_xyz, None); _cuda(xyz, "xyz")
+    B, M = new_xyz.size(0), new_xyz.size(1)
+    N = xyz.size(1)
+    idx = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    with torch.cuda.device(new_xyz.device):
+        cabi.check(_L().b200pn2_ball_query(B, N, M, float(radius), int(nsample), _p(new_xyz), _p(xyz), _p(idx),
+                                           stream_ptr()), "ball_query")
+    return idx
+
+
+def group_points(points, idx):
+    """(B,C,N) f32, (B,M,ns) i32 -> (B,C,M,ns)   [group_points.cpp:17-39]"""
+    _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")
+    _cuda(points, None); _cuda(idx, "idx")
+    B, C, N = points.shape
+    M, ns = idx.size(1), idx.size(2)
+    out = torch.empty((B, C, M, ns), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        cabi.check(_L().b200pn2_group_points(B, C, N, M, ns, _p(points), _p(idx), _p(out), stream_ptr()), "group_points")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """(B,C,M,ns) f32, idx, n -> (B,C,n)   [group_points.cpp:41-65]"""
+    _contig(grad_out, "grad_out"); _contig(idx, "idx"); _is_float(grad_out, "grad_out"); _is_int(idx, "idx")
+    _cuda(grad_out, None); _cuda(idx, "idx")
+    B, C, M, ns = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        cabi.check(_L().b200pn2_group_points_grad(B, C, int(n), M, ns, _p(grad_out), _p(idx), _p(out), stream_ptr()),
+                   "group_points_grad")
+    return out
+
+
+# ---- wide entry (no reference counterpart): fused ball-query -> group -> SharedMLP -> max -------------------
+
+def sa_forward(xyz, features, new_xyz, radius, nsample, layers, use_xyz=True, normalize_xyz=False,
+               features_pm=None, idx=None, want_idx=False, want_pm=False):
+    """Fused set-abstraction forward (include/b200_pointnet2.h: b200pn2_sa_forward).
+
+    xyz (B,N,3), features (B,C,N) or None, new_xyz (B,M,3); layers = [(weight (cout,cin), scale (cout,), shift (cout,))]
+    returns (out (B,cout,M), out_pm (B,M,cout) or None, idx (B,M,nsample) or None)."""
+    _contig(xyz, "xyz"); _contig(new_xyz, "new_xyz"); _is_float(xyz, "xyz"); _is_float(new_xyz, "new_xyz")
+    _cuda(xyz, None); _cuda(new_xyz, "new_xyz")
+    B, N = xyz.size(0), xyz.size(1)
+    M = new_xyz.size(1)
+    C = 0
+    if features is not None:
+        _contig(features, "features"); _is_float(features, "features"); _cuda(features, "features")
+        C = features.size(1)
+    if features_pm is not None:
+        _contig(features_pm, "features_pm"); _is_float(features_pm, "features_pm"); _cuda(features_pm, "features_pm")
+        C = features_pm.size(2)
+    if idx is not None:
+        _contig(idx, "idx"); _is_int(idx, "idx"); _cuda(idx, "idx")
+    arr = (cabi.MlpLayer * len(layers))()
+    keep_alive = []
+    for i, (w, sc, sh) in enumerate(layers):
+        for t, nm in ((w, "weight"), (sc, "scale"), (sh, "shift")):
+            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
+        w2 = w.reshape(w.size(0), -1)
+        keep_alive.append(w2)
+        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
+        arr[i].weight, arr[i].scale, arr[i].shift = w2.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    cout = layers[-1][0].size(0)
+    dev = xyz.device
+    out = torch.empty((B, cout, M), dtype=torch.float32, device=dev)
+    out_pm = torch.empty((B, M, cout), dtype=torch.float32, device=dev) if want_pm else None
+    idx_out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=dev) if (want_idx and idx is None) else None
+    with torch.cuda.device(dev):
+        nbytes = int(_L().b200pn2_sa_forward_workspace(B, N, M, C, int(nsample), int(features_pm is not None),
+                                                       int(idx is not None or idx_out is not None)))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes else None
+        cabi.check(_L().b200pn2_sa_forward(B, N, M, C, float(radius), int(nsample), int(bool(use_xyz)),
+                                           int(bool(normalize_xyz)), _p(xyz), _p(features), _p(features_pm),
+                                           _p(new_xyz), _p(idx), len(layers), arr, _p(out), _p(out_pm), _p(idx_out),
+                                           _p(ws), nbytes, stream_ptr()), "sa_forward")
+    return out, out_pm, (idx if idx is not None else idx_out)

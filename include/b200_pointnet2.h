@@ -1,0 +1,119 @@
+/*
+ * b200_pointnet2.h -- C ABI of the B200-native PointNet++ set-abstraction / feature-propagation
+ * operators (libb200pc.so).  Plain device pointers + sizes + a CUDA stream; no torch types.
+ *
+ * Each entry replaces one function of the reference's pybind module `pointnet2._ext`
+ * (pointnet2/_ext_src/src/bindings.cpp:11-24); the line cited at each prototype is the
+ * reference host wrapper whose behaviour it reproduces.  All tensors are contiguous, fp32
+ * data / int32 indices, resident on the current CUDA device.
+ *
+ * Return value: 0 on success, non-zero on error (b200_last_error() gives the message; the
+ * library never calls exit(), unlike cuda_utils.h:35-44 of the reference).
+ * Launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ * default stream), like the reference which launches on the current torch stream.
+ */
+#ifndef B200_POINTNET2_H
+#define B200_POINTNET2_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *b200_stream_t; /* cudaStream_t */
+
+/* library identification / error reporting */
+int b200_abi_version(void);
+const char *b200_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
+unsigned long long b200_launch_count(void);
+
+/* furthest_point_sampling(points (B,N,3), nsamples) -> idx (B,m) int32
+ * reference: sampling.cpp:70-91 + sampling_gpu.cu:74-234.
+ * idx[b][0] = 0; tie order = (min-dist desc, bit-reversed (k mod bs) asc, k asc) with
+ * bs = opt_n_threads(N) (cuda_utils.h:18-24); points with x^2+y^2+z^2 <= 1e-3 never compete.
+ * `scratch` may be NULL; otherwise >= B*N floats used only by the large-N fallback
+ * (the reference's `tmp` tensor).                                                          */
+int b200pn2_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx, float *scratch,
+                                    b200_stream_t stream);
+
+/* gather_points(points (B,C,N), idx (B,m)) -> out (B,C,m)        reference: sampling.cpp:20-44 */
+int b200pn2_gather_points(int B, int C, int N, int m, const float *points, const int32_t *idx, float *out,
+                          b200_stream_t stream);
+/* gather_points_grad(grad_out (B,C,m), idx, n) -> grad_points (B,C,N); the callee zero-fills
+ * grad_points first.                                             reference: sampling.cpp:46-69 */
+int b200pn2_gather_points_grad(int B, int C, int N, int m, const float *grad_out, const int32_t *idx,
+                               float *grad_points, b200_stream_t stream);
+
+/* ball_query(new_xyz (B,M,3), xyz (B,N,3), radius, nsample) -> idx (B,M,nsample) int32
+ * first `nsample` hits in ascending point index, padded with the first hit, zeros if empty.
+ * reference: ball_query.cpp:13-37 + ball_query_gpu.cu:14-59                                */
+int b200pn2_ball_query(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                       int32_t *idx, b200_stream_t stream);
+
+/* group_points(points (B,C,N), idx (B,M,ns)) -> out (B,C,M,ns)   reference: group_points.cpp:17-39 */
+int b200pn2_group_points(int B, int C, int N, int M, int ns, const float *points, const int32_t *idx, float *out,
+                         b200_stream_t stream);
+/* group_points_grad(grad_out (B,C,M,ns), idx, n) -> grad_points (B,C,N), zero-filled by the callee.
+ * reference: group_points.cpp:41-65                                                          */
+int b200pn2_group_points_grad(int B, int C, int N, int M, int ns, const float *grad_out, const int32_t *idx,
+                              float *grad_points, b200_stream_t stream);
+
+/* three_nn(unknown (B,n,3), known (B,m,3)) -> dist2 (B,n,3) f32 ascending, idx (B,n,3) int32
+ * reference: interpolate.cpp:19-45 + interpolate_gpu.cu:14-73 (squared distances; the Python
+ * layer takes the sqrt, pointnet2_utils.py:143)                                               */
+int b200pn2_three_nn(int B, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx,
+                     b200_stream_t stream);
+
+/* three_interpolate(points (B,C,m), idx (B,n,3), weight (B,n,3)) -> out (B,C,n)
+ * reference: interpolate.cpp:47-74 + interpolate_gpu.cu:77-116                                */
+int b200pn2_three_interpolate(int B, int C, int m, int n, const float *points, const int32_t *idx,
+                              const float *weight, float *out, b200_stream_t stream);
+/* three_interpolate_grad(grad_out (B,C,n), idx, weight, m) -> grad_points (B,C,m), zero-filled by
+ * the callee.  Implements the scatter-add gradient of interpolate_gpu.cu:121-148 (the reference host
+ * wrapper interpolate.cpp:95 launches the forward kernel by mistake; deliberate divergence).   */
+int b200pn2_three_interpolate_grad(int B, int C, int n, int m, const float *grad_out, const int32_t *idx,
+                                   const float *weight, float *grad_points, b200_stream_t stream);
+
+/* ---- fused set-abstraction forward (the wide entry; no single reference counterpart) ------------
+ * Replaces the sequence  ball_query -> group_points(xyz) -> (-centre, *1/r) -> group_points(features)
+ * -> concat -> SharedMLP (1x1 conv + eval-mode BN + ReLU, up to 3 layers) -> max over nsample
+ * of PointnetSAModuleVotes.forward (pointnet2_modules.py:215-277, pointnet2_utils.py:318-377,
+ * pytorch_utils.py:14-39) with grouped tensors kept on chip.
+ *
+ *   xyz      (B,N,3)   features (B,C,N) or NULL (C=0)   new_xyz (B,M,3)
+ *   weights  layer l: W_l (cout_l, cin_l) row-major fp32 (nn.Conv2d.weight viewed 2-D),
+ *            scale_l / shift_l (cout_l): y = relu(scale * (W x) + shift)  (BN eval folded to an
+ *            affine; scale=1, shift=bias for bn=False)
+ *   cin_0 = (use_xyz ? 3 : 0) + C ; channel order [dx,dy,dz, features...] as torch.cat in
+ *            pointnet2_utils.py:358-360
+ *   normalize_xyz: multiply relative xyz by fp32 (1/radius)                                      */
+typedef struct {
+  int cin;
+  int cout;
+  const float *weight; /* (cout, cin) */
+  const float *scale;  /* (cout) */
+  const float *shift;  /* (cout) */
+} b200_mlp_layer;
+
+/*   features     (B,C,N) channel-major (the reference layout) or NULL
+ *   features_pm  (B,N,C) point-major copy of the same data or NULL; when NULL and C % 4 == 0 the library
+ *                transposes `features` into `workspace` so that one grouped row is one aligned run
+ *   idx_in       (B,M,nsample) neighbour indices or NULL (NULL: the library runs the ball query)
+ *   out          (B,cout_last,M);  out_pm (B,M,cout_last) or NULL;  idx_out (B,M,nsample) or NULL
+ *   workspace    device scratch of at least b200pn2_sa_forward_workspace(...) bytes (may be NULL if 0)
+ * ReLU follows every layer (pytorch_utils.py:21, activation=nn.ReLU).                                   */
+size_t b200pn2_sa_forward_workspace(int B, int N, int M, int C, int nsample, int have_features_pm, int have_idx);
+
+int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                       const float *xyz, const float *features, const float *features_pm, const float *new_xyz,
+                       const int32_t *idx_in, int num_layers, const b200_mlp_layer *layers, float *out,
+                       float *out_pm, int32_t *idx_out, void *workspace, size_t workspace_bytes,
+                       b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_POINTNET2_H */

@@ -1,0 +1,253 @@
+/*
+ * oracle/pointnet2_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, fp32) of the reference's PointNet++ CUDA operators
+ * (module `pointnet2._ext` of yezhen17/3DIoUMatch).  Only tests/, the smoke()
+ * check in __graft_entry__.py and bench.py's cpu_baseline leg may load this.
+ * The product (3dioumatch_b200/csrc) never calls into it.
+ *
+ * Every function cites the reference lines it restates (paths relative to the
+ * reference tree).  Index-producing ops are restated at the level of the
+ * reference's *thread mapping and rounding sequence*, because index parity is
+ * bit-exact:
+ *   - squared distance = fmaf(dz,dz, fmaf(dx,dx, dy*dy))   (nvcc's contraction
+ *     of a*a + b*b + c*c for sm_100a; verified from the PTX/SASS of the
+ *     reference kernels, see oracle/build_ref.py --dump-fma)
+ *   - compile this file with -ffp-contract=off so gcc adds no contraction.
+ *
+ * Parity status: pinned on the GPU box against the reference's own CUDA
+ * extension built from /root/reference into oracle/_ref (tests/test_ref_cuda.py)
+ * and against tests/golden/ vectors generated from that extension.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- launch-geometry helper --------------------------------------------------
+ * pointnet2/_ext_src/src/cuda_utils.h:18-24  opt_n_threads():
+ *   pow_2 = (int)(log((double)n) / log(2.0));  clamp(1 << pow_2, 1, 512)        */
+int orc_opt_n_threads(int work_size) {
+  const int pow_2 = (int)(log((double)work_size) / log(2.0));
+  int t = 1 << pow_2;
+  if (t > 512) t = 512;
+  if (t < 1) t = 1;
+  return t;
+}
+
+static inline float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  /* (a-b)^2 summed the way the sm_100a build of the reference rounds it */
+  const float dx = ax - bx, dy = ay - by, dz = az - bz;
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  return fmaf(dz, dz, t);
+}
+
+/* ---- furthest point sampling -------------------------------------------------
+ * sampling_gpu.cu:74-178 (kernel), :64-70 (__update), sampling.cpp:70-91 (host:
+ * idx zeros, temp filled with 1e10).  One block of bs threads per scene; thread
+ * t walks k = t, t+bs, ...; strict-> running best (init -1, index 0); binary
+ * tree over shared memory, left operand wins ties.                              */
+void orc_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx) {
+  if (m <= 0) return;
+  const int bs = orc_opt_n_threads(N);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    const float *pts = xyz + (size_t)b * N * 3;
+    int32_t *out = idx + (size_t)b * m;
+    float *temp = (float *)malloc(sizeof(float) * (size_t)(N > 0 ? N : 1));
+    unsigned char *skip = (unsigned char *)malloc((size_t)(N > 0 ? N : 1));
+    float *dists = (float *)malloc(sizeof(float) * (size_t)bs);
+    int *dists_i = (int *)malloc(sizeof(int) * (size_t)bs);
+    for (int k = 0; k < N; ++k) {
+      temp[k] = 1e10f; /* sampling.cpp:78-80 */
+      const float x = pts[k * 3], y = pts[k * 3 + 1], z = pts[k * 3 + 2];
+      float mag = y * y; /* sampling_gpu.cu:105  (x*x)+(y*y)+(z*z), contracted */
+      mag = fmaf(x, x, mag);
+      mag = fmaf(z, z, mag);
+      skip[k] = ((double)mag <= 1e-3) ? 1 : 0; /* :106, double compare; NaN is not skipped */
+    }
+    int old = 0;
+    out[0] = 0; /* :92 */
+    for (int j = 1; j < m; ++j) {
+      const float x1 = pts[old * 3], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
+      for (int t = 0; t < bs; ++t) {
+        dists[t] = -1.0f; /* :96-97 best=-1, besti=0 */
+        dists_i[t] = 0;
+      }
+      for (int k = 0; k < N; ++k) { /* ascending k == ascending within each thread */
+        if (skip[k]) continue;
+        const int t = k % bs;
+        const float d = sqdist3(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2], x1, y1, z1); /* :108-109 (x2-x1) */
+        const float d2 = fminf(d, temp[k]);                                             /* :111 */
+        temp[k] = d2;
+        if (d2 > dists[t]) { /* :113-114 strict */
+          dists[t] = d2;
+          dists_i[t] = k;
+        }
+      }
+      for (int s = bs / 2; s >= 1; s >>= 1) { /* :120-173 */
+        for (int t = 0; t < s; ++t) {
+          const float v1 = dists[t], v2 = dists[t + s];
+          const int i1 = dists_i[t], i2 = dists_i[t + s];
+          dists[t] = v1 > v2 ? v1 : (v2 > v1 ? v2 : v1); /* max(v1,v2); NaN cannot occur (fminf) */
+          dists_i[t] = v2 > v1 ? i2 : i1;
+        }
+      }
+      old = dists_i[0];
+      out[j] = old; /* :175-176 */
+    }
+    free(temp);
+    free(skip);
+    free(dists);
+    free(dists_i);
+  }
+}
+
+/* ---- gather ------------------------------------------------------------------
+ * sampling_gpu.cu:13-25 / :39-52.  points (B,C,N), idx (B,m) -> out (B,C,m).    */
+void orc_gather_points(int B, int C, int N, int m, const float *points, const int32_t *idx, float *out) {
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < m; ++j)
+        out[((size_t)b * C + c) * m + j] = points[((size_t)b * C + c) * N + idx[(size_t)b * m + j]];
+}
+
+void orc_gather_points_grad(int B, int C, int N, int m, const float *grad_out, const int32_t *idx,
+                            float *grad_points /* zero-initialised (B,C,N) */) {
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < m; ++j)
+        grad_points[((size_t)b * C + c) * N + idx[(size_t)b * m + j]] += grad_out[((size_t)b * C + c) * m + j];
+}
+
+/* ---- ball query --------------------------------------------------------------
+ * ball_query_gpu.cu:14-49; host ball_query.cpp:24-26 (idx zero-initialised).
+ * new_xyz (B,M,3) centres, xyz (B,N,3) -> idx (B,M,nsample).                     */
+void orc_ball_query(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                    int32_t *idx) {
+  const float radius2 = radius * radius; /* :27 fp32 multiply */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b) {
+    for (int j = 0; j < M; ++j) {
+      const float *pts = xyz + (size_t)b * N * 3;
+      const float *c = new_xyz + ((size_t)b * M + j) * 3;
+      int32_t *row = idx + ((size_t)b * M + j) * nsample;
+      for (int l = 0; l < nsample; ++l) row[l] = 0;
+      int cnt = 0;
+      for (int k = 0; k < N && cnt < nsample; ++k) {
+        const float d2 = sqdist3(c[0], c[1], c[2], pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]); /* :36-37 (new - x) */
+        if (d2 < radius2) {                                                                      /* :38 strict */
+          if (cnt == 0)
+            for (int l = 0; l < nsample; ++l) row[l] = k; /* :39-43 */
+          row[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
+/* ---- grouping ----------------------------------------------------------------
+ * group_points_gpu.cu:13-32 / :48-68.  points (B,C,N), idx (B,M,ns) -> (B,C,M,ns) */
+void orc_group_points(int B, int C, int N, int M, int ns, const float *points, const int32_t *idx, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < M; ++j)
+        for (int k = 0; k < ns; ++k)
+          out[(((size_t)b * C + c) * M + j) * ns + k] =
+              points[((size_t)b * C + c) * N + idx[((size_t)b * M + j) * ns + k]];
+}
+
+void orc_group_points_grad(int B, int C, int N, int M, int ns, const float *grad_out, const int32_t *idx,
+                           float *grad_points /* zero-initialised (B,C,N) */) {
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int j = 0; j < M; ++j)
+        for (int k = 0; k < ns; ++k)
+          grad_points[((size_t)b * C + c) * N + idx[((size_t)b * M + j) * ns + k]] +=
+              grad_out[(((size_t)b * C + c) * M + j) * ns + k];
+}
+
+/* ---- three nearest neighbours --------------------------------------------------
+ * interpolate_gpu.cu:14-64.  unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32,
+ * idx (B,n,3).  bests are doubles initialised to 1e40, strict <.                 */
+void orc_three_nn(int B, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b) {
+    for (int j = 0; j < n; ++j) {
+      const float *u = unknown + ((size_t)b * n + j) * 3;
+      const float *kn = known + (size_t)b * m * 3;
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float d = sqdist3(u[0], u[1], u[2], kn[k * 3], kn[k * 3 + 1], kn[k * 3 + 2]); /* :38 (u - x) */
+        if (d < best1) {
+          best3 = best2; besti3 = besti2;
+          best2 = best1; besti2 = besti1;
+          best1 = d; besti1 = k;
+        } else if (d < best2) {
+          best3 = best2; besti3 = besti2;
+          best2 = d; besti2 = k;
+        } else if (d < best3) {
+          best3 = d; besti3 = k;
+        }
+      }
+      float *dd = dist2 + ((size_t)b * n + j) * 3;
+      int32_t *ii = idx + ((size_t)b * n + j) * 3;
+      dd[0] = (float)best1; dd[1] = (float)best2; dd[2] = (float)best3; /* :56-58 (1e40 -> +inf) */
+      ii[0] = besti1; ii[1] = besti2; ii[2] = besti3;
+    }
+  }
+}
+
+/* ---- three interpolate ---------------------------------------------------------
+ * interpolate_gpu.cu:77-106.  points (B,C,m), idx/weight (B,n,3) -> out (B,C,n).
+ * rounding: fma(p3,w3, fma(p1,w1, p2*w2)) (sm_100a contraction of the reference).  */
+void orc_three_interpolate(int B, int C, int m, int n, const float *points, const int32_t *idx,
+                           const float *weight, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c) {
+      const float *p = points + ((size_t)b * C + c) * m;
+      for (int j = 0; j < n; ++j) {
+        const float *w = weight + ((size_t)b * n + j) * 3;
+        const int32_t *ii = idx + ((size_t)b * n + j) * 3;
+        float t = p[ii[1]] * w[1];
+        t = fmaf(p[ii[0]], w[0], t);
+        out[((size_t)b * C + c) * n + j] = fmaf(p[ii[2]], w[2], t);
+      }
+    }
+}
+
+/* interpolate_gpu.cu:121-148: the mathematically correct scatter-add gradient.
+ * (The reference host code, interpolate.cpp:95, launches the *forward* kernel by
+ * mistake; SURVEY.md section 2a.  The product ships this true gradient.)          */
+void orc_three_interpolate_grad(int B, int C, int n, int m, const float *grad_out, const int32_t *idx,
+                                const float *weight, float *grad_points /* zero-initialised (B,C,m) */) {
+  for (int b = 0; b < B; ++b)
+    for (int c = 0; c < C; ++c) {
+      float *g = grad_points + ((size_t)b * C + c) * m;
+      for (int j = 0; j < n; ++j) {
+        const float *w = weight + ((size_t)b * n + j) * 3;
+        const int32_t *ii = idx + ((size_t)b * n + j) * 3;
+        const float go = grad_out[((size_t)b * C + c) * n + j];
+        g[ii[0]] += go * w[0];
+        g[ii[1]] += go * w[1];
+        g[ii[2]] += go * w[2];
+      }
+    }
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,150 @@
+"""GPU: the sm_100a point operators (through the C ABI / pointnet2._ext drop-in) against the CPU oracle.
+Indices (FPS, ball_query, three_nn) must be bit-exact; float outputs of the data-movement ops are exact too."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (cloud kwargs, npoint, radius, nsample)
+    "c1": (dict(seed=0, B=1, N=2000, centre=False), 128, 0.2, 32),
+    "ragged": (dict(seed=1, B=3, N=1531, dup_frac=0.05, origin_frac=0.02), 200, 0.35, 16),
+    "small": (dict(seed=2, B=2, N=300, dup_frac=0.3), 64, 0.5, 8),
+    "dups": (dict(seed=3, B=2, N=4096, dup_frac=0.5, origin_frac=0.01), 512, 0.15, 64),
+    "tiny": (dict(seed=4, B=2, N=9, extent=(1, 1, 1)), 9, 5.0, 6),
+    "mid": (dict(seed=5, B=4, N=20000, dup_frac=0.02, origin_frac=0.001), 1024, 0.3, 32),
+    "npoint_gt_n": (dict(seed=6, B=1, N=40), 64, 0.5, 4),
+}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fps_ball_query_three_nn_bit_exact(pkg, orc, name):
+    import pointnet2._ext as ext
+    kw, npoint, radius, nsample = CASES[name]
+    xyz = cases.cloud(**kw)
+    t = dev(xyz)
+    fps = ext.furthest_point_sampling(t, npoint)
+    ref_fps = orc.furthest_point_sampling(xyz, npoint)
+    assert fps.dtype == torch.int32 and tuple(fps.shape) == ref_fps.shape
+    assert np.array_equal(fps.cpu().numpy(), ref_fps), "FPS indices differ"
+
+    new_xyz_ref = np.take_along_axis(xyz, ref_fps[:, :, None].astype(np.int64), 1)
+    new_xyz = ext.gather_points(t.transpose(1, 2).contiguous(), fps).transpose(1, 2).contiguous()
+    assert np.array_equal(new_xyz.cpu().numpy(), new_xyz_ref)
+
+    bq = ext.ball_query(new_xyz, t, radius, nsample)
+    assert np.array_equal(bq.cpu().numpy(), orc.ball_query(new_xyz_ref, xyz, radius, nsample)), "ball_query differs"
+
+    d2, nn = ext.three_nn(t, new_xyz)
+    rd2, rnn = orc.three_nn(xyz, new_xyz_ref)
+    assert np.array_equal(nn.cpu().numpy(), rnn), "three_nn idx differs"
+    assert np.array_equal(d2.cpu().numpy(), rd2), "three_nn dist2 differs"
+
+
+def test_fps_every_cluster_size_agrees(pkg, orc, monkeypatch):
+    """The register-resident kernel must give the same indices for every cluster size / thread count it can pick."""
+    import os
+    import subprocess
+    import sys
+    xyz = cases.cloud(7, 2, 9000, dup_frac=0.2, origin_frac=0.01)
+    ref = orc.furthest_point_sampling(xyz, 300)
+    np.save("/tmp/_fps_xyz.npy", xyz)
+    code = ("import importlib,sys,numpy as np,torch;sys.path.insert(0,%r);p=importlib.import_module('3dioumatch_b200');"
+            "p.install_dropin();import pointnet2._ext as e;x=torch.from_numpy(np.load('/tmp/_fps_xyz.npy')).cuda();"
+            "np.save('/tmp/_fps_out.npy',e.furthest_point_sampling(x,300).cpu().numpy())") % os.path.dirname(pkg.PKG_DIR)
+    for cs in (1, 2, 4, 8, 16):
+        for th in (512, 1024):
+            env = dict(os.environ, B200_FPS_CLUSTER=str(cs), B200_FPS_THREADS=str(th))
+            r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+            if r.returncode != 0 and "needs a scratch buffer" in (r.stderr + r.stdout):
+                continue  # this (cluster, threads) pair cannot hold the cloud in registers
+            assert r.returncode == 0, r.stderr[-2000:]
+            assert np.array_equal(np.load("/tmp/_fps_out.npy"), ref), "cluster=%d threads=%d" % (cs, th)
+
+
+def test_fps_scannet_shape_full_size(pkg, orc):
+    """BASELINE config: (B,N)=(8,40000) -> 2048 samples; one scene checked against the oracle, all scenes for
+    size-independent properties (distinct indices, idx[0]=0, greedy max-min property on a sample of steps)."""
+    import pointnet2._ext as ext
+    pc = cases.scene_cloud(0, 8, 40000)[:, :, :3].copy()
+    t = dev(pc)
+    fps = ext.furthest_point_sampling(t, 2048).cpu().numpy()
+    assert (fps[:, 0] == 0).all()
+    for b in range(8):
+        assert len(np.unique(fps[b])) == 2048
+    assert np.array_equal(fps[3:4], orc.furthest_point_sampling(pc[3:4], 2048))
+    # greedy property at step j: the chosen point maximises the distance to the already chosen set
+    b = 5
+    for j in (1, 2, 17, 300, 2047):
+        chosen = pc[b, fps[b, :j]]
+        d = ((pc[b][:, None, :] - chosen[None, :, :]) ** 2).sum(-1).min(1)
+        assert d[fps[b, j]] >= d.max() * (1 - 1e-5)
+
+
+def test_group_gather_interpolate_and_grads(pkg, orc):
+    import pointnet2._ext as ext
+    rng = np.random.default_rng(0)
+    B, C, N, M, ns = 3, 37, 500, 64, 16
+    pts = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, ns)).astype(np.int32)
+    g = ext.group_points(dev(pts), dev(idx))
+    assert np.array_equal(g.cpu().numpy(), orc.group_points(pts, idx))
+    gi = rng.integers(0, N, (B, M)).astype(np.int32)
+    assert np.array_equal(ext.gather_points(dev(pts), dev(gi)).cpu().numpy(), orc.gather_points(pts, gi))
+    # gradients are atomic scatter-adds: compare with tolerance (summation order is not fixed, as in the reference)
+    go = rng.standard_normal((B, C, M, ns)).astype(np.float32)
+    got = ext.group_points_grad(dev(go), dev(idx), N).cpu().numpy()
+    assert np.allclose(got, orc.group_points_grad(go, idx, N), rtol=1e-4, atol=1e-4)
+    go2 = rng.standard_normal((B, C, M)).astype(np.float32)
+    got = ext.gather_points_grad(dev(go2), dev(gi), N).cpu().numpy()
+    assert np.allclose(got, orc.gather_points_grad(go2, gi, N), rtol=1e-4, atol=1e-4)
+    # three_interpolate: bit-exact forward (same fma sequence), toleranced backward
+    n, m = 333, 77
+    known = rng.standard_normal((B, C, m)).astype(np.float32)
+    tidx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = rng.random((B, n, 3)).astype(np.float32)
+    w /= w.sum(2, keepdims=True)
+    out = ext.three_interpolate(dev(known), dev(tidx), dev(w)).cpu().numpy()
+    assert np.array_equal(out, orc.three_interpolate(known, tidx, w))
+    go3 = rng.standard_normal((B, C, n)).astype(np.float32)
+    got = ext.three_interpolate_grad(dev(go3), dev(tidx), dev(w), m).cpu().numpy()
+    assert np.allclose(got, orc.three_interpolate_grad(go3, tidx, w, m), rtol=1e-4, atol=1e-4)
+
+
+def test_autograd_functions(pkg):
+    """pointnet2_utils Functions: gradients flow through gather/group/interpolate (torch.autograd.gradcheck-style
+    directional check in fp32)."""
+    import pointnet2.pointnet2_utils as U
+    torch.manual_seed(0)
+    feats = torch.randn(2, 4, 50, device="cuda", requires_grad=True)
+    idx = torch.randint(0, 50, (2, 6, 3), device="cuda", dtype=torch.int32)
+    out = U.grouping_operation(feats, idx)
+    out.sum().backward()
+    counts = torch.zeros(2, 50, device="cuda")
+    counts.scatter_add_(1, idx.view(2, -1).long(), torch.ones(2, 18, device="cuda"))
+    assert torch.allclose(feats.grad, counts[:, None, :].expand(2, 4, 50))
+    xyz = torch.rand(2, 50, 3, device="cuda")
+    inds = U.furthest_point_sample(xyz, 8)
+    assert inds.dtype == torch.int32 and not inds.requires_grad
+    dist, nn = U.three_nn(xyz, xyz[:, :10].contiguous())
+    assert dist.shape == (2, 50, 3) and (dist[:, :10, 0] == 0).all()
+
+
+def test_three_nn_gridconv_shape(pkg, orc):
+    """GridConv call shape (models/grid_conv_module.py:87): K*64 grid points vs 1024 seeds; one scene vs the oracle."""
+    import pointnet2._ext as ext
+    rng = np.random.default_rng(1)
+    seeds = (rng.random((2, 1024, 3)) * [8, 8, 3]).astype(np.float32)
+    grid = (rng.random((2, 256 * 64, 3)) * [8, 8, 3]).astype(np.float32)
+    d2, idx = ext.three_nn(dev(grid), dev(seeds))
+    rd2, ridx = orc.three_nn(grid[:1], seeds[:1])
+    assert np.array_equal(idx[:1].cpu().numpy(), ridx) and np.array_equal(d2[:1].cpu().numpy(), rd2)
+    d = d2.cpu().numpy()
+    assert (d[..., 0] <= d[..., 1]).all() and (d[..., 1] <= d[..., 2]).all()

@@ -1,0 +1,167 @@
+"""GPU: the fused set-abstraction forward (ball query -> group -> SharedMLP -> max on chip) against the fp32
+PyTorch restatement of the reference module math (oracle/torch_ref.py), tolerance 1e-5 (abs + rel), and the
+module-level drop-in against its own unfused path."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+ATOL, RTOL = 1e-5, 1e-5
+
+
+def dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_close(got, ref):
+    err = np.abs(got - ref)
+    bound = ATOL + RTOL * np.abs(ref)
+    assert (err <= bound).all(), "max err %.3g at ref %.3g" % (err.max(), np.abs(ref).flat[err.argmax()])
+
+
+def run_case(orc, tr, B, N, M, C, radius, ns, spec, seed, use_xyz=True, normalize=True, dup=0.0):
+    import pointnet2._ext as ext
+    xyz = cases.cloud(seed, B, N, dup_frac=dup)
+    rng = np.random.default_rng(seed + 1)
+    feats = rng.standard_normal((B, C, N)).astype(np.float32) if C else None
+    fps = orc.furthest_point_sampling(xyz, M)
+    new_xyz = np.take_along_axis(xyz, fps[:, :, None].astype(np.int64), 1)
+    full_spec = [(3 if use_xyz else 0) + C] + list(spec)
+    layers = cases.mlp_params(seed + 2, full_spec)
+    ref, ref_idx = tr.sa_forward(xyz, feats, new_xyz, radius, ns, layers, use_xyz=use_xyz, normalize_xyz=normalize)
+    trip = [(dev(w), dev(s), dev(h)) for w, s, h in tr.fold(layers)]
+    out, out_pm, idx = ext.sa_forward(dev(xyz), dev(feats), dev(new_xyz), radius, ns, trip, use_xyz=use_xyz,
+                                      normalize_xyz=normalize, want_idx=True, want_pm=True)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx), "fused ball query differs"
+    assert_close(out.cpu().numpy(), ref)
+    assert torch.equal(out_pm, out.transpose(1, 2))
+    return out
+
+
+@pytest.fixture(scope="module")
+def tr(orc):
+    import torch_ref
+    return torch_ref
+
+
+def test_c1_config(orc, tr, pkg):
+    """BASELINE configs[0]: one 2000-point cloud, npoint=128, r=0.2, ns=32, mlp=[4,32] (1 feature + xyz)."""
+    import pointnet2._ext as ext
+    xyz = cases.cloud(0, 1, 2000, centre=False)
+    feats = np.random.default_rng(1).random((1, 1, 2000)).astype(np.float32)
+    fps = orc.furthest_point_sampling(xyz, 128)
+    new_xyz = np.take_along_axis(xyz, fps[:, :, None].astype(np.int64), 1)
+    layers = cases.mlp_params(2, [4, 32])
+    ref, ref_idx = tr.sa_forward(xyz, feats, new_xyz, 0.2, 32, layers, normalize_xyz=False)
+    trip = [(dev(w), dev(s), dev(h)) for w, s, h in tr.fold(layers)]
+    out, _, idx = ext.sa_forward(dev(xyz), dev(feats), dev(new_xyz), 0.2, 32, trip, want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert_close(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape", [
+    # (B, N, M, C, radius, ns, mlp)   reduced-size versions of SA1..SA4 / vote aggregation (backbone_module.py:35-69)
+    (2, 6000, 256, 1, 0.2, 64, [64, 64, 128]),
+    (2, 2048, 200, 128, 0.4, 32, [128, 128, 256]),
+    (2, 1024, 96, 256, 0.8, 16, [128, 128, 256]),
+    (3, 512, 61, 256, 1.2, 16, [128, 128, 128]),
+    (1, 700, 50, 5, 0.5, 24, [20, 33]),          # odd widths: padding paths, nsample not dividing the tile
+    (1, 700, 50, 8, 0.5, 100, [16]),             # nsample close to the tile height
+    (2, 300, 40, 0, 0.6, 8, [16, 16, 16, 24]),   # xyz only, 4 layers
+])
+def test_sa_shapes(orc, tr, pkg, shape):
+    B, N, M, C, r, ns, spec = shape
+    run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 1000 + N, dup=0.05)
+
+
+def test_no_xyz_and_unnormalised(orc, tr, pkg):
+    run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=5, use_xyz=False, normalize=False)
+    run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=6, use_xyz=True, normalize=False)
+
+
+def test_idx_in_and_point_major_inputs(orc, tr, pkg):
+    """Caller-provided neighbour indices and a caller-provided point-major feature copy give the same result."""
+    import pointnet2._ext as ext
+    B, N, M, C, r, ns = 2, 1500, 128, 64, 0.4, 32
+    xyz = cases.cloud(9, B, N)
+    feats = np.random.default_rng(10).standard_normal((B, C, N)).astype(np.float32)
+    fps = orc.furthest_point_sampling(xyz, M)
+    new_xyz = np.take_along_axis(xyz, fps[:, :, None].astype(np.int64), 1)
+    layers = cases.mlp_params(11, [C + 3, 64, 64])
+    trip = [(dev(w), dev(s), dev(h)) for w, s, h in tr.fold(layers)]
+    a, _, idx = ext.sa_forward(dev(xyz), dev(feats), dev(new_xyz), r, ns, trip, normalize_xyz=True, want_idx=True)
+    b, _, _ = ext.sa_forward(dev(xyz), dev(feats), dev(new_xyz), r, ns, trip, normalize_xyz=True, idx=idx)
+    c, _, _ = ext.sa_forward(dev(xyz), None, dev(new_xyz), r, ns, trip, normalize_xyz=True,
+                             features_pm=dev(feats.transpose(0, 2, 1)))
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_module_dropin_fused_equals_unfused(pkg, monkeypatch):
+    """PointnetSAModuleVotes in eval mode: fused single-kernel path vs the op-by-op path on the same kernels + torch
+    (cudnn/cublas fp32, TF32 off) -- the reference's own dataflow."""
+    import pointnet2_modules as M
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    net = M.PointnetSAModuleVotes(npoint=256, radius=0.3, nsample=32, mlp=[16, 64, 64, 128], use_xyz=True,
+                                  normalize_xyz=True).cuda()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+    net.eval()
+    xyz = torch.from_numpy(cases.cloud(3, 2, 5000)).cuda()
+    feats = torch.randn(2, 16, 5000, device="cuda")
+    with torch.no_grad():
+        nx1, f1, i1 = net(xyz, feats)
+        monkeypatch.setenv("B200_SA_FUSED", "0")
+        nx2, f2, i2 = net(xyz, feats)
+    assert torch.equal(i1, i2) and torch.equal(nx1, nx2)
+    assert torch.allclose(f1, f2, atol=1e-5, rtol=1e-5)
+    # `inds` pass-through (pointnet2_modules.py:239-242)
+    monkeypatch.delenv("B200_SA_FUSED")
+    with torch.no_grad():
+        nx3, f3, i3 = net(xyz, feats, i1)
+    assert torch.equal(i3, i1) and torch.equal(f3, f1)
+
+
+def test_module_training_path_backward(pkg):
+    """Training mode (batch-statistics BN) takes the unfused, differentiable path."""
+    import pointnet2_modules as M
+    torch.manual_seed(0)
+    net = M.PointnetSAModuleVotes(npoint=64, radius=0.4, nsample=16, mlp=[8, 32, 32], use_xyz=True,
+                                  normalize_xyz=True).cuda().train()
+    xyz = torch.from_numpy(cases.cloud(4, 2, 1000)).cuda()
+    feats = torch.randn(2, 8, 1000, device="cuda", requires_grad=True)
+    _, f, _ = net(xyz, feats)
+    f.square().mean().backward()
+    assert feats.grad is not None and torch.isfinite(feats.grad).all() and feats.grad.abs().sum() > 0
+    assert net.mlp_module.layer0.conv.weight.grad is not None
+
+
+def test_fp_module(pkg, orc, tr):
+    """PointnetFPModule (three_nn + three_interpolate + SharedMLP) vs the fp32 restatement."""
+    import pointnet2_modules as M
+    import pointnet2.pytorch_utils as pt
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = np.random.default_rng(0)
+    B, n, m, C1, C2 = 2, 512, 256, 24, 40
+    unknown = cases.cloud(1, B, n)
+    known = unknown[:, :m].copy()
+    uf = rng.standard_normal((B, C1, n)).astype(np.float32)
+    kf = rng.standard_normal((B, C2, m)).astype(np.float32)
+    layers = cases.mlp_params(3, [C1 + C2, 48, 32])
+    fp = M.PointnetFPModule(mlp=[C1 + C2, 48, 32]).cuda().eval()
+    with torch.no_grad():
+        for i, ly in enumerate(layers):
+            blk = getattr(fp.mlp, "layer%d" % i)
+            blk.conv.weight.copy_(dev(ly["weight"]).view_as(blk.conv.weight))
+            blk.bn.bn.weight.copy_(dev(ly["gamma"])); blk.bn.bn.bias.copy_(dev(ly["beta"]))
+            blk.bn.bn.running_mean.copy_(dev(ly["mean"])); blk.bn.bn.running_var.copy_(dev(ly["var"]))
+        got = fp(dev(unknown), dev(known), dev(uf), dev(kf)).cpu().numpy()
+    ref = tr.fp_forward(unknown, known, uf, kf, layers)
+    err = np.abs(got - ref)
+    assert (err <= 2e-5 + 2e-5 * np.abs(ref)).all(), err.max()

@@ -7,8 +7,9 @@
 // B200 design: one thread-block CLUSTER per scene (up to 16 CTAs, chosen from the occupancy query).  Every
 // point of the scene lives in registers (x, y, z, running min distance) for the whole kernel, so an
 // iteration is: PPT fused distance updates per thread -> redux.sync arg-max in the warp -> one shared
-// memory hop in the CTA -> one 32-byte DSMEM record per peer CTA -> one cluster barrier.  Nothing touches
-// L2/HBM inside the chain except the 4-byte result store.
+// memory hop in the CTA -> one 32-byte DSMEM record per peer CTA, pushed with st.async and signalled through
+// the peer's mbarrier (no cluster-wide barrier inside the loop).  Nothing touches L2/HBM inside the chain
+// except the 4-byte result store.
 //
 // Bit-exact tie order of the reference: thread t = k mod bs of the reference
 // block keeps the first strict maximum over k = t, t+bs, ...; its shared-memory tree keeps the LEFT
@@ -35,7 +36,19 @@ static int ref_opt_n_threads(int work_size) {
   return t;
 }
 
-struct __align__(16) FpsRecord {  // what one CTA tells its peers each iteration
+#ifdef B200_FPS_PROFILE
+__device__ unsigned long long g_fps_prof[8];
+#define FPS_TICK(i)                                   \
+  do {                                                \
+    const long long _t = clock64();                   \
+    prof[i] += (unsigned long long)(_t - tprev);      \
+    tprev = _t;                                       \
+  } while (0)
+#else
+#define FPS_TICK(i)
+#endif
+
+struct __align__(16) FpsRecord {  // what one CTA tells its peers each iteration (2 x 16 B st.async)
   int v;                          // float bits of the CTA's best min-distance (negative = no candidate)
   unsigned key;                   // tie key of that point
   int k;                          // its index
@@ -43,16 +56,56 @@ struct __align__(16) FpsRecord {  // what one CTA tells its peers each iteration
   float x, y, z, w;
 };
 
+// ---- mbarrier / DSMEM primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "FPS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra FPS_DONE;\n"
+      "bra FPS_WAIT;\n"
+      "FPS_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned local_smem_addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// 16-byte remote store that also completes 16 tx-bytes on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned remote_bar, unsigned a, unsigned b,
+                                            unsigned c, unsigned d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
+
+// One thread-block cluster per scene; each thread keeps PPT points (x, y, z, running min distance) in registers,
+// and the CTA keeps a copy of its coordinates in shared memory so that a winner's xyz is one indexed LDS.
+// Per iteration:  PPT branch-free distance updates -> warp arg-max (2 x redux.sync) -> CTA arg-max through shared
+// memory -> [cluster] each CTA pushes its 32-byte record into every peer's shared memory with st.async, which also
+// signals the peer's mbarrier (complete_tx); every thread waits on its own CTA's mbarrier.  No cluster-wide barrier.
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
   constexpr int NWARP = THREADS / 32;
+  extern __shared__ float s_xyz[];  // [PPT][THREADS][3]
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned CS = cluster.num_blocks();
+  const unsigned CS = cluster.num_blocks();  // power of two
   const unsigned rank = cluster.block_rank();
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = (int)CS * THREADS;       // threads per scene; a multiple of bs, so k mod bs == g mod bs
+  const int T = (int)CS * THREADS;  // threads per scene, a power of two
+  const int log2T = 31 - __clz(T);
   const int g = (int)rank * THREADS + tid;
 
   const float *pts = xyz + (size_t)b * N * 3;
@@ -61,10 +114,19 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
   __shared__ int s_v[2][NWARP];
   __shared__ unsigned s_key[2][NWARP];
   __shared__ int s_k[2][NWARP];
-  __shared__ float s_x[2][NWARP], s_y[2][NWARP], s_z[2][NWARP];
   __shared__ FpsRecord s_slot[2][16];
+  __shared__ __align__(8) unsigned long long s_bar[2];
 
-  // ---- load this thread's points into registers -------------------------------------------
+  if (CS > 1) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();  // every CTA's barriers exist before any peer signals them
+  }
+
+  // ---- load this thread's points into registers (+ the shared-memory coordinate table) ----------------
   float px[PPT], py[PPT], pz[PPT], pt[PPT];
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
@@ -75,95 +137,150 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
       pz[p] = pts[(size_t)k * 3 + 2];
       const float mag = sq3(px[p], py[p], pz[p]);  // sampling_gpu.cu:105
       // :106 `if (mag <= 1e-3) continue;` is a double compare; a skipped point never competes.
-      // min-distance -1 makes fminf() pin it at -1, which can never beat the strict `>` against -1.
+      // min-distance -1 makes fminf() pin it at -1, which can never beat a real candidate (>= 0).
       pt[p] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;  // sampling.cpp:78-80 temp = 1e10
     } else {
       px[p] = py[p] = pz[p] = 0.f;
       pt[p] = -1.0f;
     }
+    float *sp = s_xyz + (size_t)(p * THREADS + tid) * 3;
+    sp[0] = px[p]; sp[1] = py[p]; sp[2] = pz[p];
   }
+  __syncthreads();
   const unsigned bsmask = (1u << L) - 1u;
-  const unsigned rev = L > 0 ? (__brev((unsigned)g & bsmask) >> (32 - L)) : 0u;
-  const unsigned revshift = rev << 22;
+  // tie key of point k: (bitrev_L(k mod bs) << 22) | (k >> L)   -- smaller key wins among equal distances
+  auto tie_key = [&](int k) -> unsigned {
+    const unsigned rev = L > 0 ? (__brev((unsigned)k & bsmask) >> (32 - L)) : 0u;
+    return (rev << 22) | ((unsigned)k >> L);
+  };
+  // If T is a multiple of bs, all points of a thread share (k mod bs) and ascending slot == ascending key, so the
+  // first strict maximum is already the reference's choice; otherwise exact ties inside a thread need the keys.
+  const bool thread_ties = ((unsigned)T & bsmask) != 0u;
+  auto coords_of = [&](int k, float &x, float &y, float &z) {  // k owned by this CTA
+    const int p = k >> log2T, t = (k & (T - 1)) - (int)rank * THREADS;
+    const float *sp = s_xyz + (size_t)(p * THREADS + t) * 3;
+    x = sp[0]; y = sp[1]; z = sp[2];
+  };
 
   const float x0 = pts[0], y0 = pts[1], z0 = pts[2];
   float cx = x0, cy = y0, cz = z0;  // idx[0] = 0 (:89-92)
   if (rank == 0 && tid == 0) out[0] = 0;
 
+#ifdef B200_FPS_PROFILE
+  unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#endif
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
-    // ---- distance update + per-thread strict arg-max (k ascending) ----------------------------
-    float best = -1.0f;
-    int bp = 0;
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[par], CS * (unsigned)sizeof(FpsRecord));
+    // ---- distance update + per-thread arg-max (branch-free; first strict maximum in slot order) ----------
+    // All PPT updates are independent; the arg-max is a tournament tree (depth log2 PPT instead of a PPT-long
+    // dependent chain).  The left (lower-slot) entry survives ties, i.e. "first strict maximum in slot order".
+    float tv[PPT];
+    int ts[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
       const float d = sqdist3(px[p], py[p], pz[p], cx, cy, cz);  // :108-109 (x2 - x1)
       const float d2 = fminf(d, pt[p]);                           // :111
       pt[p] = d2;
-      if (d2 > best) {  // :113-114
-        best = d2;
-        bp = p;
+      tv[p] = d2;
+      ts[p] = p;
+    }
+#pragma unroll
+    for (int s = 1; s < PPT; s *= 2) {
+#pragma unroll
+      for (int i = 0; i + s < PPT; i += 2 * s) {
+        const bool gt = tv[i + s] > tv[i];  // :113-114 strict
+        tv[i] = gt ? tv[i + s] : tv[i];
+        ts[i] = gt ? ts[i + s] : ts[i];
       }
     }
-    float bx = px[0], by = py[0], bz = pz[0];
+    // a thread without candidates keeps the reference's (best = -1, besti = 0) state
+    float best = tv[0] > -1.0f ? tv[0] : -1.0f;
+    int bp = tv[0] > -1.0f ? ts[0] : 0;
+    if (thread_ties) {  // uniform branch
+      int same = 0;
 #pragma unroll
-    for (int p = 1; p < PPT; ++p)
-      if (bp == p) {
-        bx = px[p];
-        by = py[p];
-        bz = pz[p];
+      for (int p = 0; p < PPT; ++p) same += (pt[p] == best) ? 1 : 0;
+      if (same > 1 && best >= 0.f) {  // rare: exact tie inside this thread -> smallest key
+        unsigned bkey_t = 0xffffffffu;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+          const unsigned kp = tie_key(g + p * T);
+          if (pt[p] == best && kp < bkey_t) {
+            bkey_t = kp;
+            bp = p;
+          }
+        }
       }
+    }
     const int bk = g + bp * T;
     const int v = __float_as_int(best);  // best >= +0 or == -1.0f: signed-int order == float order
-    const unsigned key = revshift | ((unsigned)bk >> L);
+    const unsigned key = tie_key(bk);
+    FPS_TICK(0);  // distance update
 
     // ---- warp arg-max: value, then tie key ------------------------------------------------------
-    const int wv = __reduce_max_sync(0xffffffffu, v);
-    const unsigned wkey = __reduce_min_sync(0xffffffffu, v == wv ? key : 0xffffffffu);
-    if (v == wv && key == wkey) {
-      s_v[par][warp] = wv;
-      s_key[par][warp] = wkey;
-      s_k[par][warp] = bk;
-      s_x[par][warp] = bx;
-      s_y[par][warp] = by;
-      s_z[par][warp] = bz;
-    }
-    __syncthreads();
-    // every warp redundantly reduces the NWARP records (no second barrier needed)
-    int cv = lane < NWARP ? s_v[par][lane] : (int)0x80000000;
-    unsigned ckey = lane < NWARP ? s_key[par][lane] : 0xffffffffu;
-    int bvv = __reduce_max_sync(0xffffffffu, cv);
-    unsigned bkey = __reduce_min_sync(0xffffffffu, cv == bvv ? ckey : 0xffffffffu);
-    int src = __ffs(__ballot_sync(0xffffffffu, cv == bvv && ckey == bkey)) - 1;
-    int wk = s_k[par][src];
-    float wx = s_x[par][src], wy = s_y[par][src], wz = s_z[par][src];
-
-    if (CS > 1) {
-      // ---- one record per peer over distributed shared memory, then the cluster barrier ---------
-      if (warp == 0 && lane < (int)CS) {
-        FpsRecord *remote = cluster.map_shared_rank(&s_slot[par][rank], lane);
-        FpsRecord r;
-        r.v = bvv; r.key = bkey; r.k = wk; r.pad = 0;
-        r.x = wx; r.y = wy; r.z = wz; r.w = 0.f;
-        *remote = r;
+    int bvv = __reduce_max_sync(0xffffffffu, v);
+    unsigned bkey = __reduce_min_sync(0xffffffffu, v == bvv ? key : 0xffffffffu);
+    int wk;
+    FPS_TICK(1);  // warp arg-max
+    if (NWARP > 1) {
+      if (v == bvv && key == bkey) {
+        s_v[par][warp] = bvv;
+        s_key[par][warp] = bkey;
+        s_k[par][warp] = bk;
       }
-      cluster.sync();
-      cv = lane < (int)CS ? s_slot[par][lane].v : (int)0x80000000;
-      ckey = lane < (int)CS ? s_slot[par][lane].key : 0xffffffffu;
+      __syncthreads();
+      // every warp redundantly reduces the NWARP records (no second barrier needed)
+      const int cv = lane < NWARP ? s_v[par][lane] : (int)0x80000000;
+      const unsigned ckey = lane < NWARP ? s_key[par][lane] : 0xffffffffu;
       bvv = __reduce_max_sync(0xffffffffu, cv);
       bkey = __reduce_min_sync(0xffffffffu, cv == bvv ? ckey : 0xffffffffu);
-      src = __ffs(__ballot_sync(0xffffffffu, cv == bvv && ckey == bkey)) - 1;
+      const int src = __ffs(__ballot_sync(0xffffffffu, cv == bvv && ckey == bkey)) - 1;
+      wk = s_k[par][src];
+    } else {
+      const int src = __ffs(__ballot_sync(0xffffffffu, v == bvv && key == bkey)) - 1;
+      wk = __shfl_sync(0xffffffffu, bk, src);
+    }
+    float wx, wy, wz;
+    FPS_TICK(2);  // CTA arg-max
+    if (CS > 1) {
+      // ---- one 32-byte record per peer over distributed shared memory, signalled through its mbarrier ----
+      if (warp == 0) {
+        coords_of(wk, wx, wy, wz);
+        if (lane < (int)CS) {
+          const unsigned dst = map_to_rank(smem_u32(&s_slot[par][rank]), (unsigned)lane);
+          const unsigned bar = map_to_rank(smem_u32(&s_bar[par]), (unsigned)lane);
+          st_async_v4(dst, bar, (unsigned)bvv, bkey, (unsigned)wk, 0u);
+          st_async_v4(dst + 16, bar, __float_as_uint(wx), __float_as_uint(wy), __float_as_uint(wz), 0u);
+        }
+      }
+      FPS_TICK(3);  // st.async issue
+      mbar_wait(&s_bar[par], (unsigned)(((j - 1) >> 1) & 1));
+      FPS_TICK(4);  // wait for the peers' records
+      const int cv = lane < (int)CS ? s_slot[par][lane].v : (int)0x80000000;
+      const unsigned ckey = lane < (int)CS ? s_slot[par][lane].key : 0xffffffffu;
+      bvv = __reduce_max_sync(0xffffffffu, cv);
+      bkey = __reduce_min_sync(0xffffffffu, cv == bvv ? ckey : 0xffffffffu);
+      const int src = __ffs(__ballot_sync(0xffffffffu, cv == bvv && ckey == bkey)) - 1;
       wk = s_slot[par][src].k;
       wx = s_slot[par][src].x;
       wy = s_slot[par][src].y;
       wz = s_slot[par][src].z;
+    } else {
+      coords_of(wk, wx, wy, wz);
     }
     if (bvv < 0) {  // every candidate skipped: the reference's besti stays 0 everywhere
       wk = 0; wx = x0; wy = y0; wz = z0;
     }
     cx = wx; cy = wy; cz = wz;
     if (rank == 0 && tid == 0) out[j] = wk;  // :175-176
+    FPS_TICK(5);  // cluster arg-max + bookkeeping
   }
+#ifdef B200_FPS_PROFILE
+  if (b == 0 && rank == 0 && tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_fps_prof[i], prof[i]);
+#endif
   if (CS > 1) cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -220,22 +337,36 @@ typedef void (*fps_fn)(int, int, int, const float *, int32_t *);
 
 template <int THREADS>
 static fps_fn pick_ppt(int ppt, int *ppt_out) {
-#define B200_FPS_CASE(P)                 \
-  if (ppt <= P) {                        \
-    *ppt_out = P;                        \
-    return fps_cluster_kernel<THREADS, P>; \
+  constexpr int MAXP = THREADS >= 512 ? 20 : 32;  // register budget: 4 registers per resident point
+#define B200_FPS_CASE(P)                     \
+  if (P <= MAXP && ppt <= P) {               \
+    *ppt_out = P;                            \
+    return fps_cluster_kernel<THREADS, (P <= MAXP ? P : 1)>; \
   }
-  B200_FPS_CASE(1) B200_FPS_CASE(2) B200_FPS_CASE(3) B200_FPS_CASE(4) B200_FPS_CASE(5) B200_FPS_CASE(6)
-  B200_FPS_CASE(8) B200_FPS_CASE(12) B200_FPS_CASE(16)
+  B200_FPS_CASE(1) B200_FPS_CASE(2) B200_FPS_CASE(4) B200_FPS_CASE(6) B200_FPS_CASE(8) B200_FPS_CASE(10)
+  B200_FPS_CASE(12) B200_FPS_CASE(16) B200_FPS_CASE(20) B200_FPS_CASE(24) B200_FPS_CASE(32)
 #undef B200_FPS_CASE
   *ppt_out = 0;
   return nullptr;
 }
 
-static int max_clusters(fps_fn fn, int threads, int cs) {
+static fps_fn pick_kernel(int threads, int ppt, int *ppt_out) {
+  switch (threads) {
+    case 32: return pick_ppt<32>(ppt, ppt_out);
+    case 64: return pick_ppt<64>(ppt, ppt_out);
+    case 128: return pick_ppt<128>(ppt, ppt_out);
+    case 256: return pick_ppt<256>(ppt, ppt_out);
+    case 512: return pick_ppt<512>(ppt, ppt_out);
+  }
+  *ppt_out = 0;
+  return nullptr;
+}
+
+static int max_clusters(fps_fn fn, int threads, int cs, size_t smem) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs;
@@ -255,6 +386,17 @@ static int max_clusters(fps_fn fn, int threads, int cs) {
 
 using namespace b200;
 
+#ifdef B200_FPS_PROFILE
+// developer hook (not part of the ABI): per-stage cycle totals of scene 0 / rank 0 / thread 0, then reset
+extern "C" int b200_debug_fps_profile(unsigned long long *out8) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_fps_prof, sizeof(unsigned long long) * 8);
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_fps_prof, z, sizeof(z));
+  return 0;
+}
+#endif
+
 extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx, float *scratch,
                                                b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -265,50 +407,62 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   int L = 0;
   while ((1 << L) < bs) ++L;
 
-  // thread count per CTA: a multiple of bs(<=512); 512 for small clouds, 1024 otherwise
-  static int force_cs = -1, force_threads = -1;
+  // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
+  // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
+  // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.
+  static int force_cs = -1, force_threads = -1, debug = 0;
   if (force_cs < 0) {
     const char *e = getenv("B200_FPS_CLUSTER");
     force_cs = e ? atoi(e) : 0;
     e = getenv("B200_FPS_THREADS");
     force_threads = e ? atoi(e) : 0;
+    debug = getenv("B200_FPS_DEBUG") != nullptr;
   }
-  int threads = (N <= 1024) ? 512 : 1024;
-  if (force_threads == 512 || force_threads == 1024) threads = force_threads;
-
-  // cluster size: the largest of {16,8,4,2,1} that (a) still lets all B scenes be co-resident (one wave) when
-  // possible and (b) holds the cloud in registers (<= 16 points per thread); small clouds stay in one CTA.
   const int sms = num_sms();
-  int best_cs = 0, best_ppt = 0;
+  int best_cs = 0, best_ppt = 0, threads = 0;
   fps_fn best_fn = nullptr;
   double best_cost = 1e300;
-  const int cs_list[5] = {16, 8, 4, 2, 1};
+  const int cs_list[5] = {1, 2, 4, 8, 16};
+  const int th_list[5] = {32, 64, 128, 256, 512};
   for (int ci = 0; ci < 5; ++ci) {
     const int cs = cs_list[ci];
     if (force_cs > 0 && cs != force_cs) continue;
-    if (cs > 1 && N < cs * threads) continue;  // do not spread fewer than one point per thread
-    const int need = ceil_div(N, cs * threads);
-    if (need > 16) continue;
-    int ppt = 0;
-    fps_fn fn = threads == 512 ? pick_ppt<512>(need, &ppt) : pick_ppt<1024>(need, &ppt);
-    if (!fn) continue;
-    if (cs > 8) {
-      if (cudaFuncSetAttribute((void *)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    for (int ti = 0; ti < 5; ++ti) {
+      const int th = th_list[ti];
+      if (force_threads > 0 && th != force_threads) continue;
+      if (cs > 1 && N < cs * th) continue;  // do not spread fewer than one point per thread
+      const int need = ceil_div(N, cs * th);
+      int ppt = 0;
+      fps_fn fn = pick_kernel(th, need, &ppt);
+      if (!fn) continue;
+      const size_t smem = sizeof(float) * 3 * (size_t)ppt * th;
+      if (smem > 200 * 1024) continue;
+      if (smem > 40 * 1024 &&
+          cudaFuncSetAttribute((void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         continue;
       }
-    }
-    int conc = cs == 1 ? sms : max_clusters(fn, threads, cs);
-    if (conc <= 0) continue;
-    const int waves = ceil_div(B, conc);
-    // per-iteration cost model (cycles): update + block reduce (+ cluster exchange)
-    const double iter = 14.0 * ppt * (threads / 128) + 260.0 + (cs > 1 ? 700.0 : 0.0);
-    const double cost = waves * iter;
-    if (cost < best_cost) {
-      best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn;
+      if (cs > 8 &&
+          cudaFuncSetAttribute((void *)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      const int conc = cs == 1 ? sms : max_clusters(fn, th, cs, smem);
+      if (conc <= 0) continue;
+      const int waves = ceil_div(B, conc);
+      const int warps_per_sched = th >= 128 ? th / 128 : 1;
+      const bool ties = ((cs * th) % bs) != 0;
+      const double iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
+                          (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 60.0 : 0.0);
+      const double cost = waves * iter;
+      if (cost < best_cost) {
+        best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th;
+      }
     }
   }
-  (void)best_ppt;
+  if (debug)
+    fprintf(stderr, "[b200 fps] B=%d N=%d m=%d -> cluster=%d threads=%d ppt=%d (model %.0f cycles/iter)\n", B, N, m,
+            best_cs, threads, best_ppt, best_cost);
 
   if (!best_fn) {
     // cloud too large for the register-resident kernel
@@ -321,7 +475,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(best_cs, B, 1);
   cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(float) * 3 * (size_t)best_ppt * threads;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

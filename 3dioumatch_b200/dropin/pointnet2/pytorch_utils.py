@@ -111,7 +111,18 @@ class SharedMLP(nn.Sequential):
     # ---- export for the fused kernel ---------------------------------------------------------------------
     def fold_affine(self):
         """[(weight (cout,cin), scale (cout,), shift (cout,))] such that each block is relu(scale*(W x)+shift),
-        or None when a block is not conv(1x1) -> [eval BN] -> ReLU."""
+        or None when a block is not conv(1x1) -> [eval BN] -> ReLU.  Cached until a parameter/buffer changes
+        (tensor version counters) or the module switches between train() and eval()."""
+        stamp = tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers())) + \
+            tuple(m.training for m in self.modules())
+        cached = getattr(self, "_b200_fold_cache", None)
+        if cached is not None and cached[0] == stamp:
+            return cached[1]
+        result = self._fold_affine_uncached()
+        object.__setattr__(self, "_b200_fold_cache", (stamp, result))
+        return result
+
+    def _fold_affine_uncached(self):
         triples = []
         for block in self.children():
             conv = bnorm = act = None

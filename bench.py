@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/sec of the VoteNet forward + IoU hot path (BASELINE.json `metric`, configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this package (hand-written sm_100a kernels)
+  python bench.py --impl reference ...                            # the unmodified reference operator stack (oracle/_ref)
+  torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU, scenes sharded, no data-path collective
+
+A step = one forward of the VoteNet-with-IoU-branch dataflow (3dioumatch_b200/harness.py) over one batch of
+B=8 synthetic ScanNet-shaped scenes (N=40000 points, C=4, 256 proposals) + IoU labels against 64 padded GT boxes.
+Prints ONE JSON line on rank 0 (keys: see the task contract; extra keys `breakdown_ms`, `reference_cuda`, `c3`).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_SCENES, N_POINTS, N_PROPOSAL, N_GT = 8, 40000, 256, 64
+N_ROTATE = 32  # distinct input batches cycled through the timed region: 32 x 5.1 MB = 164 MB > 126 MB of L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref", action="store_true", help="skip the in-run timing of the reference CUDA ops")
+    ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="consecutive steps alternate between this many CUDA streams (software pipelining across steps)")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not run the FPS index chain on a side stream")
+    ap.add_argument("--batch", type=int, default=B_SCENES)
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                              ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def load_stack(impl):
+    if impl == "reference":
+        ref_root = os.path.join(ROOT, "oracle", "_ref")
+        if not os.path.exists(os.path.join(ref_root, "pointnet2", "_ext.so")):
+            return None
+        harness = importlib.import_module("3dioumatch_b200.harness")
+        return harness, harness.stack_from_path(ref_root)
+    harness = importlib.import_module("3dioumatch_b200.harness")
+    return harness, harness.stack_b200()
+
+
+# ---- per-operator timing (serialised, CUDA events) for the breakdown and the roofline of the dominant kernel ----
+def breakdown(net, ops, pcs, gt, torch, iters=3):
+    import pointnet2._ext as ext
+    records = {}
+
+    def wrap(name, fn, bytes_fn):
+        def inner(*a, **k):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            torch.cuda.synchronize()
+            key = name + bytes_fn(*a, **k)[0]
+            rec = records.setdefault(key, {"ms": 0.0, "calls": 0, "bytes": bytes_fn(*a, **k)[1], "flops": bytes_fn(*a, **k)[2]})
+            rec["ms"] += e0.elapsed_time(e1)
+            rec["calls"] += 1
+            return out
+        return inner
+
+    def b_fps(points, m):
+        B, N = points.shape[0], points.shape[1]
+        return "[N=%d,m=%d]" % (N, m), B * (N * 12 + m * 4), 10.0 * B * N * m
+
+    def b_bq(new_xyz, xyz, r, ns):
+        B, M, N = new_xyz.shape[0], new_xyz.shape[1], xyz.shape[1]
+        return "[N=%d,M=%d]" % (N, M), B * ((N + M) * 12 + M * ns * 4), 8.0 * B * N * M
+
+    def b_sa(xyz, features, new_xyz, radius, nsample, layers, **kw):
+        B, N, M = xyz.shape[0], xyz.shape[1], new_xyz.shape[1]
+        C = features.shape[1] if features is not None else 0
+        wsum = sum(int(w.shape[0]) * int(w.reshape(w.shape[0], -1).shape[1]) for w, _, _ in layers)
+        cout = int(layers[-1][0].shape[0])
+        by = B * (N * 12 + N * C * 4 + M * 12 + M * 4 + M * cout * 4) + wsum * 4
+        return "[N=%d,M=%d,ns=%d]" % (N, M, nsample), by, 2.0 * B * M * nsample * wsum + 8.0 * B * N * M
+
+    def b_nn(u, k):
+        B, n, m = u.shape[0], u.shape[1], k.shape[1]
+        return "[n=%d,m=%d]" % (n, m), B * ((n + m) * 12 + n * 24), 8.0 * B * n * m
+
+    def b_ti(p, idx, w):
+        B, C, n = p.shape[0], p.shape[1], idx.shape[1]
+        return "[C=%d,n=%d]" % (C, n), B * n * (24 + 16 * C), 6.0 * B * C * n
+
+    def b_gather(p, idx):
+        B, C, m = p.shape[0], p.shape[1], idx.shape[1]
+        return "[C=%d,m=%d]" % (C, m), B * m * (4 + 8 * C), 0.0
+
+    saved = {}
+    for name, bf in (("furthest_point_sampling", b_fps), ("ball_query", b_bq), ("sa_forward", b_sa),
+                     ("three_nn", b_nn), ("three_interpolate", b_ti), ("gather_points", b_gather)):
+        saved[name] = getattr(ext, name)
+        setattr(ext, name, wrap(name, saved[name], bf))
+    try:
+        with torch.no_grad():
+            for i in range(iters):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                net(pcs[i % len(pcs)], gt)
+                e1.record()
+                torch.cuda.synchronize()
+                records.setdefault("_step_serialised", {"ms": 0.0, "calls": 0, "bytes": 0, "flops": 0})
+                records["_step_serialised"]["ms"] += e0.elapsed_time(e1)
+                records["_step_serialised"]["calls"] += 1
+    finally:
+        for name, fn in saved.items():
+            setattr(ext, name, fn)
+    out = {}
+    for k, r in records.items():
+        per = r["ms"] / max(r["calls"], 1)
+        out[k] = {"ms": round(per, 4), "calls_per_step": r["calls"] // iters, "alg_bytes": int(r["bytes"]),
+                  "alg_flops": float(r["flops"])}
+    return out
+
+
+def cpu_baseline(torch, points):
+    """The oracle port (oracle/*.c + fp32 torch-CPU MLPs) on the host cores: ONE scene of the same workload."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import oracle as orc
+    import torch_ref
+    orc.build()
+    pc = cases.scene_cloud(123, 1, points)
+    xyz, feat = np.ascontiguousarray(pc[:, :, :3]), np.ascontiguousarray(pc[:, :, 3:].transpose(0, 2, 1))
+    t0 = time.time()
+    cfg = [(2048, 0.2, 64, [1 + 3, 64, 64, 128]), (1024, 0.4, 32, [131, 128, 128, 256]),
+           (512, 0.8, 16, [259, 128, 128, 256]), (256, 1.2, 16, [259, 128, 128, 256])]
+    levels = []
+    for i, (m, r, ns, spec) in enumerate(cfg):
+        inds = orc.furthest_point_sampling(xyz, m)
+        new_xyz = np.take_along_axis(xyz, inds[:, :, None].astype(np.int64), 1)
+        feat, _ = torch_ref.sa_forward(xyz, feat, new_xyz, r, ns, cases.mlp_params(i, spec), normalize_xyz=True)
+        xyz = new_xyz
+        levels.append((xyz, feat))
+    f = torch_ref.fp_forward(levels[2][0], levels[3][0], levels[2][1], levels[3][1], cases.mlp_params(10, [512, 256, 256]))
+    f = torch_ref.fp_forward(levels[1][0], levels[2][0], levels[1][1], f, cases.mlp_params(11, [512, 256, 256]))
+    seed_xyz = levels[1][0]
+    inds = orc.furthest_point_sampling(seed_xyz, N_PROPOSAL)
+    agg_xyz = np.take_along_axis(seed_xyz, inds[:, :, None].astype(np.int64), 1)
+    torch_ref.sa_forward(seed_xyz, f, agg_xyz, 0.3, 16, cases.mlp_params(12, [259, 128, 128, 128]), normalize_xyz=True)
+    grid = (np.random.default_rng(0).random((1, N_PROPOSAL * 64, 3)) * [8, 8, 3] - [4, 4, 0]).astype(np.float32)
+    d2, idx = orc.three_nn(grid, seed_xyz)
+    w = np.full((1, N_PROPOSAL * 64, 3), 1 / 3, np.float32)
+    interp = orc.three_interpolate(f, idx, w)
+    x = torch.from_numpy(np.concatenate([np.zeros((1, 3, N_PROPOSAL * 64), np.float32), interp], 1)).view(1, 259, N_PROPOSAL, 64)
+    torch_ref.shared_mlp(x, cases.mlp_params(13, [259, 128, 128, 128]))
+    orc.boxes_iou3d(cases.boxes(0, N_PROPOSAL), cases.boxes(1, N_GT))
+    dt = time.time() - t0
+    return {"value": round(1.0 / dt, 4), "unit": "scenes/s", "cores": int(orc.num_threads()), "kind": "port",
+            "sample": "1 scene (N=%d) through oracle/*.c index ops (OpenMP) + fp32 torch-CPU shared MLPs, %.1f s" % (points, dt)}
+
+
+def main():
+    a = parse()
+    import numpy as np
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference" and world > 1 and rank != 0:
+        return 0  # the reference arm runs on rank 0 only
+    distributed = world > 1 and a.impl != "reference"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    loaded = load_stack(a.impl)
+    if loaded is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference CUDA extensions) not built"}))
+        return 0
+    harness, ops = loaded
+    net = harness.make_model(ops, seed=1, num_proposal=N_PROPOSAL, device=dev)
+    net.backbone.prefetch = not a.no_prefetch
+    B, N = a.batch, a.points
+    lanes = [torch.cuda.Stream() for _ in range(max(a.lanes, 1))]
+
+    # ---- inputs: N_ROTATE distinct batches per rank, pinned on the host and resident on the device -------------
+    base_pc, base_gt = harness.make_inputs(B, N, N_GT, seed=rank)
+    rng = np.random.default_rng(1000 + rank)
+    host_pcs = []
+    for i in range(N_ROTATE):
+        pc = base_pc.copy()
+        pc[:, :, :3] += rng.normal(0, 0.01, (B, 1, 3)).astype(np.float32)  # distinct data per batch, same geometry
+        pc = pc[:, rng.permutation(N)] if i else pc
+        host_pcs.append(torch.from_numpy(np.ascontiguousarray(pc)).pin_memory())
+    host_gt = torch.from_numpy(base_gt).pin_memory()
+    dev_pcs = [t.to(dev) for t in host_pcs]
+    dev_gt = host_gt.to(dev)
+    out_keys = ("iou_labels", "iou_scores", "center", "size", "heading", "objectness")
+    cabi = importlib.import_module("3dioumatch_b200._cabi") if a.impl == "b200" else None
+
+    def step_resident(i):
+        with torch.cuda.stream(lanes[i % len(lanes)]):
+            return net(dev_pcs[i % N_ROTATE], dev_gt)
+
+    host_out = [dict() for _ in lanes]
+
+    def step_e2e(i):
+        lane = i % len(lanes)
+        with torch.cuda.stream(lanes[lane]):
+            pc = host_pcs[i % N_ROTATE].to(dev, non_blocking=True)
+            gt = host_gt.to(dev, non_blocking=True)
+            res = net(pc, gt)
+            for k in out_keys:
+                if k not in host_out[lane]:
+                    host_out[lane][k] = torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True)
+                host_out[lane][k].copy_(res[k], non_blocking=True)
+        return res
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for s_ in lanes:
+            s_.wait_stream(cur)          # every lane starts after the start event
+        for i in range(steps):
+            fn(i)
+        for s_ in lanes:
+            cur.wait_stream(s_)          # the stop event waits for all lanes (and their side streams)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if distributed:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    with torch.no_grad():
+        for i in range(max(a.warmup, 3)):
+            step_resident(i)
+            step_e2e(i)
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = cabi.launch_count() if cabi else 0
+        ms_res = timed(step_resident, a.steps)
+        launches = (cabi.launch_count() - launches0) if cabi else 0
+        ms_e2e = timed(step_e2e, a.steps)
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    scenes = world * B * a.steps if distributed else B * a.steps
+    n_gpus = world if distributed else 1
+    value = scenes / (ms_res / 1e3)
+    e2e_value = scenes / (ms_e2e / 1e3)
+    h2d = int(host_pcs[0].numel() * 4 + host_gt.numel() * 4)
+    d2h = int(sum(v.numel() * v.element_size() for v in host_out[0].values()))
+    line = {
+        "metric": "scenes/sec VoteNet fwd+IoU (B=8, N=40000)", "value": round(value, 3), "unit": "scenes/s",
+        "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_res / a.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": a.impl,
+        "config": {"workload": "configs[1]: ScanNet-shaped synthetic (B=%d,N=%d,C=4) VoteNet-IoU-branch forward dataflow, "
+                               "%d proposals, IoU labels vs %d GT slots; random-init weights, eval-mode BN" % (B, N, N_PROPOSAL, N_GT),
+                   "scenes_per_gpu_per_step": B, "lanes": len(lanes),
+                   "prefetch_fps_chain": bool(net.backbone.prefetch), "parallelism": "scene-sharded x%d, no data-path collective" % n_gpus,
+                   "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (N_ROTATE, N_ROTATE * B * N * 16 / 1e6),
+                   "tf32": "torch defaults (cudnn conv TF32 allowed) for the torch-side 1x1 convs; all libb200pc kernels fp32"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / a.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        if a.impl == "b200" and not a.no_breakdown:
+            with torch.no_grad():
+                bd = breakdown(net, ops, dev_pcs, dev_gt, torch)
+            line["breakdown_ms"] = {k: v for k, v in bd.items()}
+            ours = {k: v for k, v in bd.items() if not k.startswith("_")}
+            top = max(ours, key=lambda k: ours[k]["ms"] * max(ours[k]["calls_per_step"], 1))
+            t = ours[top]
+            ach = t["alg_bytes"] / (t["ms"] / 1e3) / 1e9
+            line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": round(ach, 3), "peak": hbm_peak,
+                                "unit": "GB/s", "frac": round(ach / hbm_peak, 5), "traffic": None,
+                                "peak_source": peak_src, "launch_ms": t["ms"],
+                                "achieved_fp32_tflops": round(t["alg_flops"] / (t["ms"] / 1e3) / 1e12, 3),
+                                "note": "algorithmic bytes / launch time; this kernel is latency/FP32-bound, not HBM-bound "
+                                        "(DESIGN.md section 4)"}
+        if a.impl == "reference":
+            line["cpu_baseline"] = {"value": line["value"], "unit": "scenes/s", "kind": "reference",
+                                    "cores": os.cpu_count(),
+                                    "sample": "unmodified reference CUDA ops (oracle/_ref, built from /root/reference) on "
+                                              "cuda:0 -- the reference has no CPU implementation of this path; host cores "
+                                              "only drive the launches"}
+            line["e2e"]["h2d_bytes_per_step"] = h2d
+        elif n_gpus == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(torch, N)
+        if a.impl == "b200" and n_gpus == 1 and not a.no_ref:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6",
+                                    "--warmup", "3", "--batch", str(B), "--points", str(N), "--lanes", str(a.lanes)] +
+                                   (["--no-prefetch"] if a.no_prefetch else []),
+                                   capture_output=True, text=True, timeout=600,
+                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                line["reference_cuda"] = {"value": ref.get("value"), "e2e": ref.get("e2e", {}).get("value"),
+                                          "ms_per_step": ref.get("ms_per_step"), "unit": "scenes/s",
+                                          "what": "unmodified reference pointnet2/_ext + iou3d_nms CUDA ops on the same GPU, same dataflow"}
+                if ref.get("value"):
+                    line["speedup_vs_reference_cuda"] = round(line["value"] / ref["value"], 3)
+            except Exception as e:  # the reference arm is informational here
+                line["reference_cuda"] = {"unavailable": str(e)[:200]}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

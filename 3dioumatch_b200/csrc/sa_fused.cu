@@ -329,6 +329,11 @@ __global__ void __launch_bounds__(256) transpose_cn_kernel(int C, int N, const f
 
 int ball_query_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
                       int32_t *idx, cudaStream_t stream);
+// sa_tc.cu: the tcgen05 (tensor-core) version of the gather -> MLP -> max stage
+bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm);
+int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
+                 const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
+                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -398,6 +403,9 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
     fpm = t;
   }
   const bool vec_ok = fpm && (C & 3) == 0 && ((((uintptr_t)fpm) & 15) == 0);
+  if (vec_ok && sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm))
+    return sa_tc_launch(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, fpm, new_xyz, idx, num_layers, layers,
+                        out, out_pm, stream);
 
   SaParams p;
   p.B = B; p.N = N; p.M = M; p.C = C; p.ns = nsample; p.use_xyz = use_xyz ? 1 : 0; p.nl = num_layers;

@@ -1,0 +1,30 @@
+"""Drives each libb200pc kernel a few times at the BASELINE shapes (for `ncu --set full` captures)."""
+import importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch, cases
+pkg = importlib.import_module("3dioumatch_b200"); pkg.install_dropin()
+import pointnet2._ext as ext
+from pcdet.ops.iou3d_nms import iou3d_nms_utils as iu
+B = 8
+pc = cases.scene_cloud(0, B, 40000)
+xyz = torch.from_numpy(pc[:, :, :3].copy()).cuda()
+feat = torch.from_numpy(pc[:, :, 3:].transpose(0, 2, 1).copy()).cuda()
+def layers(spec):
+    return [(torch.from_numpy(l["weight"]).cuda(), torch.from_numpy(l["gamma"]).cuda(), torch.from_numpy(l["beta"]).cuda())
+            for l in cases.mlp_params(0, spec)]
+for it in range(3):
+    i1 = ext.furthest_point_sampling(xyz, 2048)
+    x1 = ext.gather_points(xyz.transpose(1, 2).contiguous(), i1).transpose(1, 2).contiguous()
+    f1, f1pm, _ = ext.sa_forward(xyz, feat, x1, 0.2, 64, layers([4, 64, 64, 128]), normalize_xyz=True, want_pm=True)
+    i2 = ext.furthest_point_sampling(x1, 1024)
+    x2 = ext.gather_points(x1.transpose(1, 2).contiguous(), i2).transpose(1, 2).contiguous()
+    f2, _, _ = ext.sa_forward(x1, f1, x2, 0.4, 32, layers([131, 128, 128, 256]), normalize_xyz=True)
+    grid = torch.rand(B, 256 * 64, 3, device="cuda") * 6 - 3
+    d2, idx = ext.three_nn(grid, x2)
+    w = torch.full((B, 256 * 64, 3), 1 / 3, device="cuda")
+    ext.three_interpolate(f2, idx, w)
+    a = torch.from_numpy(cases.boxes(0, 2048)).cuda(); b = torch.from_numpy(cases.boxes(1, 512, jitter_of=cases.boxes(0, 2048)[:512])).cuda()
+    iu.boxes_iou3d_gpu(a, b)
+torch.cuda.synchronize()
+print("done")

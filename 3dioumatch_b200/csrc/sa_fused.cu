@@ -345,7 +345,7 @@ extern "C" size_t b200pn2_sa_forward_workspace(int B, int N, int M, int C, int n
                                                int have_idx) {
   size_t bytes = 0;
   if (!have_idx) bytes += align256(sizeof(int32_t) * (size_t)B * M * nsample);
-  if (!have_features_pm && C > 0 && (C & 3) == 0) bytes += align256(sizeof(float) * (size_t)B * N * C);
+  if (!have_features_pm && C > 1) bytes += align256(sizeof(float) * (size_t)B * N * C);
   return bytes;
 }
 
@@ -392,7 +392,8 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
                                  cudaMemcpyDeviceToDevice, stream));
   }
   const float *fpm = features_pm;
-  if (C > 0 && (C & 3) == 0 && !fpm) {
+  if (C == 1 && !fpm) fpm = features;  // (B,1,N) and (B,N,1) are the same memory
+  if (C > 1 && !fpm) {
     const size_t need = align256(sizeof(float) * (size_t)B * N * C);
     B200_CHECK_ARG(ws && off + need <= workspace_bytes, "sa_forward: workspace too small (features_pm)");
     float *t = (float *)(ws + off);
@@ -403,7 +404,7 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
     fpm = t;
   }
   const bool vec_ok = fpm && (C & 3) == 0 && ((((uintptr_t)fpm) & 15) == 0);
-  if (vec_ok && sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm))
+  if (sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm))
     return sa_tc_launch(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, fpm, new_xyz, idx, num_layers, layers,
                         out, out_pm, stream);
 

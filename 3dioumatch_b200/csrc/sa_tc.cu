@@ -38,6 +38,7 @@ constexpr uint32_t TC_WSTAGE_BYTES = 2 * TC_KB_BYTES;  // W_hi | W_lo
 struct TcLayer {
   const float *scale, *shift;
   int cin, cout, nkb, nhalf;
+  int rows;           // weight rows per stage = MMA N (cout for hidden layers, <= 128 per half for the last layer)
   size_t packed_off;  // byte offset of this layer's stages in the packed weight buffer
 };
 
@@ -48,13 +49,14 @@ struct TcParams {
   const int32_t *idx;
   float *out, *out_pm;
   const uint8_t *packed;
+  int vec_gather;  // feature rows are 16-byte aligned runs of a multiple of 4 floats
   TcLayer L[TC_MAXL];
 };
 
 // ---- weight packing: (cout, cin) fp32 -> [half][kb][hi|lo][128 rows x 128 B, 128-byte swizzle] -----------------------
 struct PackParams {
   const float *w[TC_MAXL];
-  int cin[TC_MAXL], cout[TC_MAXL], nkb[TC_MAXL], nhalf[TC_MAXL];
+  int cin[TC_MAXL], cout[TC_MAXL], nkb[TC_MAXL], nhalf[TC_MAXL], rows[TC_MAXL];
   size_t off[TC_MAXL];
   int nl, perm_c;  // perm_c >= 0: layer 0 column k reads source channel (k < perm_c ? 3 + k : k - perm_c)
 };
@@ -62,9 +64,10 @@ struct PackParams {
 __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint8_t *__restrict__ packed) {
   const int l = blockIdx.y;
   if (l >= p.nl) return;
-  const int items = p.nhalf[l] * p.nkb[l] * 128 * 8;  // (half, kb, row, chunk)
+  const int rows = p.rows[l];
+  const int items = p.nhalf[l] * p.nkb[l] * rows * 8;  // (half, kb, row, chunk)
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    const int chunk = it & 7, row = (it >> 3) & 127, rest = it >> 10;
+    const int chunk = it & 7, row = (it >> 3) % rows, rest = (it >> 3) / rows;
     const int kb = rest % p.nkb[l], half = rest / p.nkb[l];
     const int n = half * 128 + row;
     float v[4], hi[4], lo[4];
@@ -76,12 +79,27 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint
       v[e] = (n < p.cout[l] && k < p.cin[l]) ? p.w[l][(size_t)n * p.cin[l] + src] : 0.f;
       tc::split_tf32(v[e], hi[e], lo[e]);
     }
-    uint8_t *stage = packed + p.off[l] + (size_t)(half * p.nkb[l] + kb) * TC_WSTAGE_BYTES;
+    const size_t stage_bytes = (size_t)rows * 256;  // hi rows | lo rows, 128 B each
+    uint8_t *stage = packed + p.off[l] + (size_t)(half * p.nkb[l] + kb) * stage_bytes;
     const uint32_t off = tc::sw128_offset(row, chunk);
     *reinterpret_cast<float4 *>(stage + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4 *>(stage + TC_KB_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4 *>(stage + (size_t)rows * 128 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
+
+#ifdef B200_TC_PROFILE
+__device__ unsigned long long g_tc_prof[16];
+#define TC_TICK(i)                                                   \
+  do {                                                               \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {            \
+      const long long _t = clock64();                                \
+      g_tc_prof[i] += (unsigned long long)(_t - tc_prev);            \
+      tc_prev = _t;                                                  \
+    }                                                                \
+  } while (0)
+#else
+#define TC_TICK(i)
+#endif
 
 // ---- the fused kernel -----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) {
@@ -91,8 +109,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
   uint8_t *R2 = base + 8 * TC_KB_BYTES;     // 2 x 32 KB
   float *s_scale = reinterpret_cast<float *>(R2 + 2 * TC_WSTAGE_BYTES);  // [TC_MAXL][256]
   float *s_shift = s_scale + TC_MAXL * 256;
+  float *s_slab = s_shift + TC_MAXL * 256;  // [128][36] transpose slab of the final epilogue (its own region: the
+                                            // epilogue of half 0 runs while half 1's MMAs still read R1 and R2)
 
-  __shared__ uint64_t full_a[2], empty_a[2], full_w[2], empty_w[2], accum_full, x_ready;
+  __shared__ uint64_t full_a[2], empty_a[2], full_w[2], empty_w[2], accum_full, x_ready, accum_half[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -111,6 +131,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       tc::mbar_init(&empty_w[s], 1);
     }
     tc::mbar_init(&accum_full, 1);
+    tc::mbar_init(&accum_half[0], 1);
+    tc::mbar_init(&accum_half[1], 1);
     tc::mbar_init(&x_ready, 128);
     tc::mbar_fence_init();
   }
@@ -133,18 +155,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       for (int l = 0; l < nl; ++l) {
         const int nst = p.L[l].nhalf * p.L[l].nkb;
         const uint8_t *src = p.packed + p.L[l].packed_off;
+        const uint32_t stage_bytes = (uint32_t)p.L[l].rows * 256u;
         for (int s = 0; s < nst; ++s, ++i) {
           const int st = i & 1;
           tc::mbar_wait(&empty_w[st], (uint32_t)(((i >> 1) & 1) ^ 1));
-          tc::mbar_arrive_expect_tx(&full_w[st], TC_WSTAGE_BYTES);
-          tc::bulk_g2s(R2 + st * TC_WSTAGE_BYTES, src + (size_t)s * TC_WSTAGE_BYTES, TC_WSTAGE_BYTES, &full_w[st]);
+          tc::mbar_arrive_expect_tx(&full_w[st], stage_bytes);
+          tc::bulk_g2s(R2 + st * TC_WSTAGE_BYTES, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
         }
       }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128);
       int i = 0;  // flat weight-stage counter (same order as the loader)
       int acc_use = 0, xr_use = 0;
       for (int l = 0; l < nl; ++l) {
@@ -154,6 +176,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
           tc::tc_fence_after_sync();
         }
         const int nkb = p.L[l].nkb;
+        const uint32_t idesc = tc::make_idesc_tf32(128, p.L[l].rows);
+        const uint32_t wlo_off = (uint32_t)p.L[l].rows * 128u;
         for (int h = 0; h < p.L[l].nhalf; ++h) {
           const uint32_t d_addr = tmem_d + (uint32_t)(h * 128);
           for (int kb = 0; kb < nkb; ++kb, ++i) {
@@ -170,7 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
             }
             tc::mbar_wait(&full_w[ws], (uint32_t)((i >> 1) & 1));
             tc::tc_fence_after_sync();
-            const uint32_t w_hi = tc::smem_addr(R2 + ws * TC_WSTAGE_BYTES), w_lo = w_hi + TC_KB_BYTES;
+            const uint32_t w_hi = tc::smem_addr(R2 + ws * TC_WSTAGE_BYTES), w_lo = w_hi + wlo_off;
             const uint64_t da_hi = tc::make_desc_sw128(a_hi), da_lo = tc::make_desc_sw128(a_lo);
             const uint64_t dw_hi = tc::make_desc_sw128(w_hi), dw_lo = tc::make_desc_sw128(w_lo);
 #pragma unroll
@@ -183,14 +207,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
             if (l == 0) tc::mma_commit(&empty_a[kb & 1]);
             tc::mma_commit(&empty_w[ws]);
           }
+          if (l == nl - 1) tc::mma_commit(&accum_half[h]);  // the final epilogue of half h overlaps half h+1's MMAs
         }
-        tc::mma_commit(&accum_full);
+        if (l < nl - 1) tc::mma_commit(&accum_full);
         ++acc_use;
       }
       (void)acc_use;
     }
   } else {
     // ================= workers: row `tid` of the tile =================
+#ifdef B200_TC_PROFILE
+    long long tc_prev = clock64();
+#endif
     const int row = tid;
     const int g = row / ns;
     const bool valid = g < g_here;
@@ -202,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
     }
     const int C = p.C;
-    const float *frow = valid ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
+    const float *frow = (valid && C > 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
     float rel[3] = {0.f, 0.f, 0.f};
     if (valid && p.use_xyz) {
       const float *q = p.xyz + ((size_t)b * p.N + src_idx) * 3;
@@ -212,16 +240,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       rel[2] = __fmul_rn(__fsub_rn(q[2], ctr[2]), p.inv_r);
     }
     // ---- layer-1 A operand: [features (C) | rel xyz (3) | 0 ...], two stages of one k-block each ----
-    for (int kb = 0; kb < nkb1; ++kb) {
-      const int as = kb & 1;
-      tc::mbar_wait(&empty_a[as], (uint32_t)(((kb >> 1) & 1) ^ 1));
-      uint8_t *a_hi = R1 + as * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
-      float4 v[8];
+    // The global loads of k-block kb+1 are issued before k-block kb is split and stored (register double buffer),
+    // so the L2 latency of the gather overlaps the CUDA-core work and the tensor-core work of the previous block.
+    auto load_kb = [&](int kb, float4 (&v)[8]) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int ch = kb * 32 + c * 4;
-        if (valid && ch + 3 < C) {
-          v[c] = *reinterpret_cast<const float4 *>(frow + ch);
+        if (valid && p.vec_gather && ch + 3 < C) {
+          v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
         } else {
           float t[4];
 #pragma unroll
@@ -237,6 +263,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
           v[c] = make_float4(t[0], t[1], t[2], t[3]);
         }
       }
+    };
+    auto store_kb = [&](int kb, const float4 (&v)[8]) {
+      const int as = kb & 1;
+      tc::mbar_wait(&empty_a[as], (uint32_t)(((kb >> 1) & 1) ^ 1));
+      uint8_t *a_hi = R1 + as * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float4 h, l;
@@ -248,93 +279,148 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full_a[as]);
+    };
+    {
+      float4 va[8], vb[8];
+      load_kb(0, va);
+      for (int kb = 0; kb < nkb1; kb += 2) {
+        if (kb + 1 < nkb1) load_kb(kb + 1, vb);
+        store_kb(kb, va);
+        if (kb + 1 < nkb1) {
+          if (kb + 2 < nkb1) load_kb(kb + 2, va);
+          store_kb(kb + 1, vb);
+        }
+      }
     }
+    TC_TICK(0);  // layer-1 gather (all k-blocks issued)
     // ---- epilogues ----
     for (int l = 0; l < nl; ++l) {
-      tc::mbar_wait(&accum_full, (uint32_t)(l & 1));
-      tc::tc_fence_after_sync();
+      if (l < nl - 1) {
+        tc::mbar_wait(&accum_full, (uint32_t)(l & 1));
+        tc::tc_fence_after_sync();
+      }
+      TC_TICK(1 + 2 * l);  // waited for layer l's MMAs
       const float *sc = s_scale + l * 256, *sh = s_shift + l * 256;
       const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
       if (l + 1 < nl) {
         // hidden layer: X = relu(scale*acc+shift) -> split -> R1 as the next layer's K-major operand
         uint8_t *x_hi = R1, *x_lo = R1 + 4 * TC_KB_BYTES;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32], r2[32];
-          tc::tmem_ld_32x32(lane_addr + (uint32_t)c0, r);
-          tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)c0, r2);
-          tc::tmem_ld_wait();
+        uint32_t ra[32], ra2[32], rb[32], rb2[32];
+        tc::tmem_ld_32x32(lane_addr, ra);
+        tc::tmem_ld_32x32(lane_addr + 256u, ra2);
+        auto emit = [&](int c0, const uint32_t (&r)[32], const uint32_t (&r2)[32]) {
           uint8_t *kb_hi = x_hi + (c0 >> 5) * TC_KB_BYTES, *kb_lo = x_lo + (c0 >> 5) * TC_KB_BYTES;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
+            const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
+            const float scv[4] = {s4.x, s4.y, s4.z, s4.w}, shv[4] = {h4.x, h4.y, h4.z, h4.w};
             float y[4], h[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int col = c0 + c * 4 + e;
               const float acc = __uint_as_float(r[c * 4 + e]) + __uint_as_float(r2[c * 4 + e]);
-              y[e] = fmaxf(fmaf(acc, sc[col], sh[col]), 0.f);
+              y[e] = fmaxf(fmaf(acc, scv[e], shv[e]), 0.f);
               tc::split_tf32(y[e], h[e], lo[e]);
             }
             const uint32_t off = tc::sw128_offset(row, c);
             *reinterpret_cast<float4 *>(kb_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4 *>(kb_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
+        };
+        const int H = p.L[l].cout;  // hidden width, multiple of 32
+        for (int c0 = 0; c0 < H; c0 += 64) {
+          tc::tmem_ld_wait();  // ra ready
+          if (c0 + 32 < H) {
+            tc::tmem_ld_32x32(lane_addr + (uint32_t)(c0 + 32), rb);
+            tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)(c0 + 32), rb2);
+          }
+          emit(c0, ra, ra2);
+          if (c0 + 32 < H) {
+            tc::tmem_ld_wait();  // rb ready
+            if (c0 + 64 < H) {
+              tc::tmem_ld_32x32(lane_addr + (uint32_t)(c0 + 64), ra);
+              tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)(c0 + 64), ra2);
+            }
+            emit(c0 + 32, rb, rb2);
+          }
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before_sync();
         tc::mbar_arrive(&x_ready);
+        TC_TICK(2 + 2 * l);  // hidden epilogue of layer l
       } else {
-        // last layer: relu(scale*acc+shift), max over the nsample rows of each centre, write (B,cout,M) [+ (B,M,cout)]
+        // last layer: relu(scale*acc+shift) -> shared slab [128 rows][32 cols] ->
+        // thread (centre g, column j) takes the max over the centre's nsample rows -> (B,cout,M) [+ (B,M,cout)]
         const int cout = p.L[l].cout;
-        const unsigned gmask = ns >= 32 ? 0xffffffffu : (lane < 16 ? 0x0000ffffu : 0xffff0000u);
-        const int gl = ns >= 32 ? warp : warp * 2 + (lane >> 4);  // centre (within the tile) of this lane's rows
+        float *slab = s_slab;  // pitch 36 floats: conflict-free STS.128 / LDS
+        constexpr int PITCH = 36;
+        const int G = p.G;                             // centres per tile (128 / ns)
         for (int c0 = 0; c0 < cout; c0 += 32) {
+          if ((c0 & 127) == 0) {
+            tc::mbar_wait(&accum_half[c0 >> 7], 0u);
+            tc::tc_fence_after_sync();
+          }
           uint32_t r[32], r2[32];
           tc::tmem_ld_32x32(lane_addr + (uint32_t)c0, r);
           tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)c0, r2);
           tc::tmem_ld_wait();
-          float keep0 = 0.f, keep1 = 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // previous slab fully consumed
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
-            const float acc = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
-            const float y = fmaxf(fmaf(acc, sc[col], sh[col]), 0.f);  // >= 0: int order == float order
-            const int mx = __reduce_max_sync(gmask, __float_as_int(y));
-            if (ns >= 32) {
-              if (lane == j) keep0 = __int_as_float(mx);
-            } else {
-              if ((lane & 15) == (j & 15)) {
-                if (j < 16) keep0 = __int_as_float(mx); else keep1 = __int_as_float(mx);
-              }
-            }
+          for (int c = 0; c < 8; ++c) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
+            const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
+            float4 y;
+            y.x = fmaxf(fmaf(__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]), s4.x, h4.x), 0.f);
+            y.y = fmaxf(fmaf(__uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]), s4.y, h4.y), 0.f);
+            y.z = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
+            y.w = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
+            *reinterpret_cast<float4 *>(slab + row * PITCH + c * 4) = y;
           }
-          if (gl < g_here) {
-            const int m = m0 + gl;
-            if (ns >= 32) {
-              const int col = c0 + lane;
-              if (col < cout) {
-                p.out[((size_t)b * cout + col) * p.M + m] = keep0;
-                if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + col] = keep0;
-              }
-            } else {
-              const int cA = c0 + (lane & 15), cB = cA + 16;
-              if (cA < cout) {
-                p.out[((size_t)b * cout + cA) * p.M + m] = keep0;
-                if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cA] = keep0;
-              }
-              if (cB < cout) {
-                p.out[((size_t)b * cout + cB) * p.M + m] = keep1;
-                if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cB] = keep1;
-              }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // slab written
+          for (int o = tid; o < G * 32; o += 128) {
+            const int gg = o >> 5, j = o & 31;
+            const float *col = slab + (gg * ns) * PITCH + j;
+            float mx0 = col[0], mx1 = mx0, mx2 = mx0, mx3 = mx0;
+            int s2 = 0;
+            for (; s2 + 4 <= ns; s2 += 4) {  // independent loads: the LDS latency is paid once per 4 rows
+              mx0 = fmaxf(mx0, col[(s2 + 0) * PITCH]);
+              mx1 = fmaxf(mx1, col[(s2 + 1) * PITCH]);
+              mx2 = fmaxf(mx2, col[(s2 + 2) * PITCH]);
+              mx3 = fmaxf(mx3, col[(s2 + 3) * PITCH]);
+            }
+            for (; s2 < ns; ++s2) mx0 = fmaxf(mx0, col[s2 * PITCH]);
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            if (gg < g_here) {
+              const int m = m0 + gg, cc = c0 + j;
+              p.out[((size_t)b * cout + cc) * p.M + m] = mx;
+              if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cc] = mx;
             }
           }
         }
+        TC_TICK(2 + 2 * l);  // final epilogue (max-reduce + store)
       }
     }
   }
+#ifdef B200_TC_PROFILE
+  if (warp < 4) {
+    long long tc_prev = 0;
+    (void)tc_prev;
+  }
+#endif
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tc::tmem_dealloc<512>(tmem_d);
 }
+
+#ifdef B200_TC_PROFILE
+extern "C" int b200_debug_tc_profile(unsigned long long *out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 // Can the tensor-core kernel take this stage?  (hidden widths 128, last 128|256, nsample 16|32, aligned point-major features)
 bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm) {
@@ -344,14 +430,16 @@ bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200
     enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (!enabled) return false;
-  if (!(nsample == 16 || nsample == 32)) return false;
+  if (nsample < 8 || nsample > 128 || (128 % nsample) != 0) return false;
   if (num_layers < 2 || num_layers > TC_MAXL) return false;
-  if (C < 32 || (C & 3) || !feat_pm || (((uintptr_t)feat_pm) & 15)) return false;
+  if (C > 0 && !feat_pm) return false;
   if (layers[0].cin != C + (use_xyz ? 3 : 0)) return false;
   for (int l = 0; l < num_layers; ++l) {
     const bool last = l == num_layers - 1;
-    if (last ? !(layers[l].cout == 128 || layers[l].cout == 256) : layers[l].cout != 128) return false;
-    if (l > 0 && layers[l].cin != 128) return false;
+    const int co = layers[l].cout;
+    if (co % 32 != 0 || co < 32) return false;
+    if (last ? !(co <= 128 || co == 256) : co > 128) return false;
+    if (l > 0 && layers[l].cin != layers[l - 1].cout) return false;
   }
   return true;
 }
@@ -365,6 +453,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   p.nl = num_layers;
   p.inv_r = normalize_xyz ? (float)(1.0 / (double)radius) : 1.0f;
   p.xyz = xyz; p.feat_pm = feat_pm; p.new_xyz = new_xyz; p.idx = idx; p.out = out; p.out_pm = out_pm;
+  p.vec_gather = (C > 0 && (C & 3) == 0 && ((((uintptr_t)feat_pm) & 15) == 0)) ? 1 : 0;
   size_t off = 0;
   pk.nl = num_layers;
   pk.perm_c = use_xyz ? C : -1;
@@ -373,17 +462,25 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     t.scale = layers[l].scale; t.shift = layers[l].shift; t.cin = layers[l].cin; t.cout = layers[l].cout;
     t.nkb = (layers[l].cin + 31) / 32;
     t.nhalf = (layers[l].cout + 127) / 128;
+    // rows per stage: the whole layer when it fits one MMA (<= 128), else two equal halves of 128
+    t.rows = layers[l].cout <= 128 ? layers[l].cout : 128;
+    if (layers[l].cout > 128 && layers[l].cout != 256) {
+      set_error("sa_forward(tc): last-layer width %d unsupported", layers[l].cout);
+      return 1;
+    }
     t.packed_off = off;
     pk.w[l] = layers[l].weight; pk.cin[l] = t.cin; pk.cout[l] = t.cout; pk.nkb[l] = t.nkb; pk.nhalf[l] = t.nhalf;
+    pk.rows[l] = t.rows;
     pk.off[l] = off;
-    off += (size_t)t.nhalf * t.nkb * TC_WSTAGE_BYTES;
+    off += (size_t)t.nhalf * t.nkb * (size_t)t.rows * 256;
   }
   uint8_t *packed = nullptr;
   B200_CUDA_OK(cudaMallocAsync((void **)&packed, off, stream));
   tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
-  const size_t smem = 1024 + 8 * TC_KB_BYTES + 2 * TC_WSTAGE_BYTES + 2 * TC_MAXL * 256 * sizeof(float);
+  const size_t smem = 1024 + 8 * TC_KB_BYTES + 2 * TC_WSTAGE_BYTES + 2 * TC_MAXL * 256 * sizeof(float) +
+                      128 * 36 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -34,6 +34,9 @@ PROTOTYPES = {
     "b200pn2_sa_forward": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_interp_mlp_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
     "b200iou_boxes_overlap_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200iou_boxes_iou_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200iou_boxes_iou3d": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -90,6 +90,11 @@ ball_query_kernel(int N, int M, float radius2, int nsample, const float *__restr
   }
 }
 
+// ball_query_grid.cu
+bool ball_query_grid_wanted(int B, int N, int M, float radius);
+int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                           int32_t *idx, cudaStream_t stream);
+
 // shared with sa_fused.cu
 int ball_query_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
                       int32_t *idx, cudaStream_t stream) {
@@ -98,6 +103,8 @@ int ball_query_launch(int B, int N, int M, float radius, int nsample, const floa
   if (B == 0 || M == 0 || nsample == 0) return 0;
   B200_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
   B200_CHECK_ARG(B <= 65535, "ball_query: B=%d exceeds grid.y", B);
+  if (ball_query_grid_wanted(B, N, M, radius))
+    return ball_query_grid_launch(B, N, M, radius, nsample, new_xyz, xyz, idx, stream);
   const float radius2 = radius * radius;  // ball_query_gpu.cu:27, one fp32 multiply
   dim3 grid(ceil_div(M, BQ_WARPS * BQ_QW), B);
   ball_query_kernel<<<grid, BQ_WARPS * 32, 0, stream>>>(N, M, radius2, nsample, new_xyz, xyz, idx);

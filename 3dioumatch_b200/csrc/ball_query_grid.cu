@@ -1,0 +1,230 @@
+// ball_query_grid.cu -- radius search for large clouds through a hashed uniform grid (sm_100a).
+//
+// The brute-force kernel (ball_query.cu) tests every centre against every point: 82 M tests per ScanNet scene for SA1.
+// With a grid of cell size >= radius only the 27 neighbouring cells can hold hits (~100-300 candidates per centre).
+// The reference's output contract (ball_query_gpu.cu:28-48) is preserved exactly:
+//   "the first `nsample` hits in ASCENDING POINT INDEX, padded with the first hit, zeros when the ball is empty"
+// because (i) the hit predicate is the same pinned fp32 expression d2 < r*r on the same operands, (ii) every point with
+// |p - c| < r lies in one of the 27 cells around c's cell (cell size > r; the cell index is a monotone function of the
+// coordinate), and (iii) the kept indices are the `nsample` smallest of the hit set, extracted in ascending order
+// (duplicates from hash collisions are skipped by the strict "greater than the previous" rule).
+//
+// Pipeline (all on `stream`): hash cell keys -> cub::DeviceRadixSort (stable, so buckets list points in ascending
+// index) -> bucket boundaries -> one warp per centre gathers candidates from 27 buckets, then selects.
+// A centre whose candidate hits overflow the per-warp list falls back to the exact brute-force scan inside the same warp.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/b200_pointnet2.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int BG_WARPS = 8;
+constexpr int BG_CAP = 512;  // hits kept per centre before selection (indices, shared memory)
+
+__device__ __forceinline__ int cell_of(float x, float inv_cell) {
+  return __float2int_rd(x * inv_cell);  // saturating; NaN -> 0
+}
+__device__ __forceinline__ unsigned cell_hash(int ix, int iy, int iz, unsigned mask) {
+  return (((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u)) & mask;
+}
+
+__global__ void __launch_bounds__(256)
+bg_key_kernel(int N, int total, float inv_cell, unsigned mask, int table_bits, const float *__restrict__ xyz,
+              unsigned *__restrict__ keys, int *__restrict__ vals) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / N, k = i - b * N;
+  const float *p = xyz + (size_t)i * 3;
+  keys[i] = ((unsigned)b << table_bits) | cell_hash(cell_of(p[0], inv_cell), cell_of(p[1], inv_cell), cell_of(p[2], inv_cell), mask);
+  vals[i] = k;
+}
+
+__global__ void __launch_bounds__(256)
+bg_bounds_kernel(int total, const unsigned *__restrict__ keys, int *__restrict__ start, int *__restrict__ end) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const unsigned k = keys[i];
+  if (i == 0 || keys[i - 1] != k) start[k] = i;
+  if (i == total - 1 || keys[i + 1] != k) end[k] = i + 1;
+}
+
+// after the sort: bucket-contiguous (x, y, z, index) records, so a candidate is ONE coalesced 16-byte load
+__global__ void __launch_bounds__(256)
+bg_reorder_kernel(int N, int total, const float *__restrict__ xyz, const unsigned *__restrict__ keys,
+                  const int *__restrict__ vals, int table_bits, float4 *__restrict__ sorted_pts) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(keys[i] >> table_bits), k = vals[i];
+  const float *p = xyz + ((size_t)b * N + k) * 3;
+  sorted_pts[i] = make_float4(p[0], p[1], p[2], __int_as_float(k));
+}
+
+__global__ void __launch_bounds__(BG_WARPS * 32)
+bg_query_kernel(int N, int M, float radius2, int nsample, float inv_cell, unsigned mask, int table_bits,
+                const float *__restrict__ new_xyz, const float *__restrict__ xyz, const float4 *__restrict__ sorted_pts,
+                const int *__restrict__ start, const int *__restrict__ end, int32_t *__restrict__ idx) {
+  __shared__ int s_hits[BG_WARPS][BG_CAP];
+  __shared__ int s_bs[BG_WARPS][32], s_bo[BG_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * BG_WARPS + warp;
+  if (c >= M) return;  // whole warp
+  const float *pts = xyz + (size_t)b * N * 3;
+  const float *ctr = new_xyz + ((size_t)b * M + c) * 3;
+  const float cx = ctr[0], cy = ctr[1], cz = ctr[2];
+  int32_t *row = idx + ((size_t)b * M + c) * nsample;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int *hits = s_hits[warp];
+
+  // the cell cover argument needs |x * inv_cell| small enough for fp32 (see header); otherwise scan exactly
+  bool overflow = !(fabsf(cx * inv_cell) < 5e4f && fabsf(cy * inv_cell) < 5e4f && fabsf(cz * inv_cell) < 5e4f);
+  const int ix = cell_of(cx, inv_cell), iy = cell_of(cy, inv_cell), iz = cell_of(cz, inv_cell);
+  // lanes 0..26: one neighbour bucket each (start, length); exclusive prefix of the lengths
+  int bs = 0, blen = 0;
+  if (lane < 27) {
+    const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+    const unsigned key = ((unsigned)b << table_bits) | cell_hash(ix + dx, iy + dy, iz + dz, mask);
+    bs = start[key];
+    blen = end[key] - bs;
+    // the same bucket reached twice (hash collision between neighbour cells): scan it once
+  }
+  for (int j = 0; j < 27; ++j) {
+    const int obs = __shfl_sync(0xffffffffu, bs, j), olen = __shfl_sync(0xffffffffu, blen, j);
+    if (lane > j && lane < 27 && olen > 0 && obs == bs) blen = 0;
+  }
+  int incl = blen;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  s_bs[warp][lane] = bs;
+  s_bo[warp][lane] = incl - blen;  // exclusive offset
+  __syncwarp();
+
+  int cnt = 0;
+  for (int q0 = 0; q0 < total && !overflow; q0 += 32) {
+    const int q = q0 + lane;
+    bool hit = false;
+    int k = 0;
+    if (q < total) {
+      int j = 0;
+#pragma unroll
+      for (int t = 1; t < 27; ++t) j = (s_bo[warp][t] <= q) ? t : j;  // offsets are non-decreasing
+      const float4 P = __ldg(sorted_pts + s_bs[warp][j] + (q - s_bo[warp][j]));
+      k = __float_as_int(P.w);
+      hit = sqdist3(cx, cy, cz, P.x, P.y, P.z) < radius2;  // ball_query_gpu.cu:36-38
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const int add = __popc(m);
+    if (cnt + add > BG_CAP) {
+      overflow = true;
+      break;
+    }
+    if (hit) hits[cnt + __popc(m & lt_mask)] = k;
+    cnt += add;
+  }
+  __syncwarp();
+
+  if (overflow) {
+    // exact brute-force scan in index order (same logic as ball_query_kernel, one centre per warp)
+    int have = 0, first = 0;
+    for (int k0 = 0; k0 < N && have < nsample; k0 += 32) {
+      const int k = k0 + lane;
+      bool hit = false;
+      if (k < N) hit = sqdist3(cx, cy, cz, pts[(size_t)k * 3], pts[(size_t)k * 3 + 1], pts[(size_t)k * 3 + 2]) < radius2;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        if (have == 0) first = k0 + __ffs(m) - 1;
+        const int slot = have + __popc(m & lt_mask);
+        if (hit && slot < nsample) row[slot] = k;
+        have += __popc(m);
+      }
+    }
+    for (int l = min(have, nsample) + lane; l < nsample; l += 32) row[l] = first;
+    return;
+  }
+
+  // ---- the nsample smallest indices of the hit list, ascending; duplicates (hash collisions) skipped ----------
+  int prev = -1, first = 0, t = 0;
+  for (; t < nsample; ++t) {
+    int best = 0x7fffffff;
+    for (int i = lane; i < cnt; i += 32) {
+      const int v = hits[i];
+      if (v > prev && v < best) best = v;
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best == 0x7fffffff) break;
+    if (t == 0) first = best;
+    if (lane == 0) row[t] = best;
+    prev = best;
+  }
+  for (int l = t + lane; l < nsample; l += 32) row[l] = first;  // pad with the first hit; all zeros when empty
+}
+
+// Workspace layout (bytes): keys[2][total] u32, vals[2][total] i32, sorted_pts[total] float4, start/end[B << table_bits]
+// i32, cub temp.
+static size_t bg_workspace_bytes(int B, int N, int table_bits, size_t *cub_bytes) {
+  const size_t total = (size_t)B * N;
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
+                                  (int *)nullptr, (int)total, 0, 32);
+  *cub_bytes = temp;
+  return 4 * total * 4 + total * 16 + 2 * ((size_t)B << table_bits) * 4 + ((temp + 255) & ~(size_t)255) + 1024;
+}
+
+bool ball_query_grid_wanted(int B, int N, int M, float radius) {
+  // B200_BQ_GRID: 0 = never, 1 = always (when representable), unset = large clouds only
+  const char *e = getenv("B200_BQ_GRID");
+  const int mode = e ? (atoi(e) ? 1 : 0) : 2;
+  if (mode == 0 || !(radius > 0.f) || N < 64) return false;
+  int bits = 1;
+  while ((1 << bits) < 2 * N) ++bits;
+  int bbits = 0;
+  while ((1 << bbits) < B) ++bbits;
+  if (bits + bbits > 31) return false;
+  return mode == 1 || N >= 8192;
+}
+
+int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
+                           int32_t *idx, cudaStream_t stream) {
+  int table_bits = 1;
+  while ((1 << table_bits) < 2 * N) ++table_bits;
+  int bbits = 0;
+  while ((1 << bbits) < B) ++bbits;
+  const unsigned mask = (1u << table_bits) - 1u;
+  const int total = B * N;
+  const float cell = radius * 1.01f + 1e-6f;  // strictly larger than the radius (1% slack absorbs fp32 rounding)
+  const float inv_cell = 1.0f / cell;
+  const float radius2 = radius * radius;  // ball_query_gpu.cu:27
+
+  size_t cub_bytes = 0;
+  const size_t ws_bytes = bg_workspace_bytes(B, N, table_bits, &cub_bytes);
+  char *ws = nullptr;
+  B200_CUDA_OK(cudaMallocAsync((void **)&ws, ws_bytes, stream));
+  unsigned *keys_in = (unsigned *)ws, *keys_out = keys_in + total;
+  int *vals_in = (int *)(keys_out + total), *vals_out = vals_in + total;
+  float4 *sorted_pts = (float4 *)(vals_out + total);  // 16-byte aligned: 4 * total * 4 bytes precede it
+  int *start = (int *)(sorted_pts + total), *end = start + ((size_t)B << table_bits);
+  void *cub_temp = (void *)(((uintptr_t)(end + ((size_t)B << table_bits)) + 255) & ~(uintptr_t)255);
+
+  bg_key_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(N, total, inv_cell, mask, table_bits, xyz, keys_in, vals_in);
+  B200_LAUNCH_OK("bg_key_kernel");
+  B200_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_in, keys_out, vals_in, vals_out, total, 0,
+                                               table_bits + bbits, stream));
+  count_launch(4);  // radix sort passes (approximate; CUB-internal kernels)
+  B200_CUDA_OK(cudaMemsetAsync(start, 0, 2 * ((size_t)B << table_bits) * sizeof(int), stream));
+  bg_bounds_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(total, keys_out, start, end);
+  B200_LAUNCH_OK("bg_bounds_kernel");
+  bg_reorder_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(N, total, xyz, keys_out, vals_out, table_bits, sorted_pts);
+  B200_LAUNCH_OK("bg_reorder_kernel");
+  dim3 grid(ceil_div(M, BG_WARPS), B);
+  bg_query_kernel<<<grid, BG_WARPS * 32, 0, stream>>>(N, M, radius2, nsample, inv_cell, mask, table_bits, new_xyz, xyz,
+                                                      sorted_pts, start, end, idx);
+  B200_LAUNCH_OK("bg_query_kernel");
+  B200_CUDA_OK(cudaFreeAsync(ws, stream));
+  return 0;
+}
+
+}  // namespace b200

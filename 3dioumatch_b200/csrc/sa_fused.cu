@@ -333,13 +333,44 @@ int ball_query_launch(int B, int N, int M, float radius, int nsample, const floa
 bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm);
 int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
                  const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
-                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream);
+                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream,
+                 const int32_t *idx3 = nullptr, const float *w3 = nullptr, const float *rel3 = nullptr);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace b200
 
 using namespace b200;
+
+// Feature-propagation rows through the same fused MLP + max kernel: row (centre g, sample s) =
+// [rel_xyz (3) | sum_t weight_t * known_feats[idx_t] (C)]  (models/grid_conv_module.py:87-113 of the reference:
+// three_nn -> inverse-distance weights -> gather/blend -> cat(relative grid) -> SharedMLP -> max over the 64 grid points)
+extern "C" int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample, int C, const float *known_feats,
+                                          const float *known_feats_pm, const int32_t *idx3, const float *weight3,
+                                          const float *rel_xyz, int num_layers, const b200_mlp_layer *layers,
+                                          float *out, void *workspace, size_t workspace_bytes, b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(B >= 0 && m_known > 0 && M >= 0 && C > 0 && (C & 3) == 0, "interp_mlp_forward: bad sizes");
+  B200_CHECK_ARG(idx3 && weight3 && out && layers && (known_feats || known_feats_pm), "interp_mlp_forward: null pointer");
+  B200_CHECK_ARG(B <= 65535, "interp_mlp_forward: B=%d exceeds grid.y", B);
+  if (B == 0 || M == 0) return 0;
+  const int use_xyz = rel_xyz ? 1 : 0;
+  const float *fpm = known_feats_pm;
+  if (!fpm) {
+    const size_t need = align256(sizeof(float) * (size_t)B * m_known * C);
+    B200_CHECK_ARG(workspace && need <= workspace_bytes, "interp_mlp_forward: workspace too small");
+    float *t = (float *)workspace;
+    dim3 grid(ceil_div(m_known, 32), ceil_div(C, 32), B);
+    transpose_cn_kernel<<<grid, 256, 0, stream>>>(C, m_known, known_feats, t);
+    B200_LAUNCH_OK("transpose_cn_kernel");
+    fpm = t;
+  }
+  B200_CHECK_ARG((((uintptr_t)fpm) & 15) == 0, "interp_mlp_forward: point-major features must be 16-byte aligned");
+  B200_CHECK_ARG(sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm),
+                 "interp_mlp_forward: layer widths / nsample not supported by the tensor-core kernel");
+  return sa_tc_launch(B, m_known, M, C, 1.0f, nsample, use_xyz, 0, nullptr, fpm, nullptr, nullptr, num_layers, layers, out,
+                      nullptr, stream, idx3, weight3, rel_xyz);
+}
 
 extern "C" size_t b200pn2_sa_forward_workspace(int B, int N, int M, int C, int nsample, int have_features_pm,
                                                int have_idx) {

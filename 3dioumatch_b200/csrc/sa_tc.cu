@@ -50,6 +50,12 @@ struct TcParams {
   float *out, *out_pm;
   const uint8_t *packed;
   int vec_gather;  // feature rows are 16-byte aligned runs of a multiple of 4 floats
+  // mode 1 (feature-propagation style rows, models/grid_conv_module.py:87-108): row (centre g, sample s) is the
+  // inverse-distance blend of three source rows, channels [rel xyz (3) | sum_t w_t * feat[idx_t] (C)]
+  int mode;
+  const int32_t *idx3;   // (B, M*ns, 3)
+  const float *w3;       // (B, M*ns, 3)
+  const float *rel3;     // (B, M*ns, 3) or NULL
   TcLayer L[TC_MAXL];
 };
 
@@ -224,15 +230,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
     const bool valid = g < g_here;
     int src_idx = -1;
     float ctr[3] = {0.f, 0.f, 0.f};
-    if (valid) {
+    if (valid && p.mode == 0) {
       src_idx = p.idx[((size_t)b * p.M + m0 + g) * ns + (row - g * ns)];
       const float *c = p.new_xyz + ((size_t)b * p.M + m0 + g) * 3;
       ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
     }
     const int C = p.C;
-    const float *frow = (valid && C > 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
+    const float *frow = (valid && C > 0 && p.mode == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
     float rel[3] = {0.f, 0.f, 0.f};
-    if (valid && p.use_xyz) {
+    const float *f3[3] = {nullptr, nullptr, nullptr};
+    float wt[3] = {0.f, 0.f, 0.f};
+    if (p.mode == 1 && valid) {
+      const size_t q = ((size_t)b * p.M + m0 + g) * ns + (row - g * ns);
+      for (int t = 0; t < 3; ++t) {
+        f3[t] = p.feat_pm + ((size_t)b * p.N + p.idx3[q * 3 + t]) * C;
+        wt[t] = p.w3[q * 3 + t];
+      }
+      if (p.rel3 && p.use_xyz) {
+        rel[0] = p.rel3[q * 3 + 0]; rel[1] = p.rel3[q * 3 + 1]; rel[2] = p.rel3[q * 3 + 2];
+      }
+    }
+    if (valid && p.use_xyz && p.mode == 0) {
       const float *q = p.xyz + ((size_t)b * p.N + src_idx) * 3;
       // pointnet2_utils.py:351-353: grouped_xyz -= new_xyz ; /= radius  (x * fp32(1/r) on CUDA)
       rel[0] = __fmul_rn(__fsub_rn(q[0], ctr[0]), p.inv_r);
@@ -246,7 +264,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int ch = kb * 32 + c * 4;
-        if (valid && p.vec_gather && ch + 3 < C) {
+        if (valid && p.mode == 1 && ch + 3 < C) {  // blend of the three neighbours (three_interpolate + concat)
+          const float4 a0 = __ldg(reinterpret_cast<const float4 *>(f3[0] + ch));
+          const float4 a1 = __ldg(reinterpret_cast<const float4 *>(f3[1] + ch));
+          const float4 a2 = __ldg(reinterpret_cast<const float4 *>(f3[2] + ch));
+          // interpolate_gpu.cu:100-104 rounding: fma(p3,w3, fma(p1,w1, p2*w2))
+          v[c].x = __fmaf_rn(a2.x, wt[2], __fmaf_rn(a0.x, wt[0], __fmul_rn(a1.x, wt[1])));
+          v[c].y = __fmaf_rn(a2.y, wt[2], __fmaf_rn(a0.y, wt[0], __fmul_rn(a1.y, wt[1])));
+          v[c].z = __fmaf_rn(a2.z, wt[2], __fmaf_rn(a0.z, wt[0], __fmul_rn(a1.z, wt[1])));
+          v[c].w = __fmaf_rn(a2.w, wt[2], __fmaf_rn(a0.w, wt[0], __fmul_rn(a1.w, wt[1])));
+        } else if (valid && p.mode == 0 && p.vec_gather && ch + 3 < C) {
           v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
         } else {
           float t[4];
@@ -255,8 +282,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
             const int k = ch + e;
             float x = 0.f;
             if (valid) {
-              if (k < C) x = frow[k];
-              else if (p.use_xyz && k < C + 3) x = rel[k - C];
+              if (k < C) {
+                x = p.mode == 0 ? frow[k]
+                                : __fmaf_rn(f3[2][k], wt[2], __fmaf_rn(f3[0][k], wt[0], __fmul_rn(f3[1][k], wt[1])));
+              } else if (p.use_xyz && k < C + 3) {
+                x = rel[k - C];
+              }
             }
             t[e] = x;
           }
@@ -446,8 +477,11 @@ bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200
 
 int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
                  const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
-                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream) {
+                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream, const int32_t *idx3,
+                 const float *w3, const float *rel3) {
   TcParams p;
+  p.mode = idx3 ? 1 : 0;
+  p.idx3 = idx3; p.w3 = w3; p.rel3 = rel3;
   PackParams pk;
   p.B = B; p.N = N; p.M = M; p.C = C; p.ns = nsample; p.G = TC_ROWS / nsample; p.use_xyz = use_xyz ? 1 : 0;
   p.nl = num_layers;

@@ -199,3 +199,45 @@ def sa_forward(xyz, features, new_xyz, radius, nsample, layers, use_xyz=True, no
                                            _p(new_xyz), _p(idx), len(layers), arr, _p(out), _p(out_pm), _p(idx_out),
                                            _p(ws), nbytes, stream_ptr()), "sa_forward")
     return out, out_pm, (idx if idx is not None else idx_out)
+
+
+def _layer_array(layers):
+    arr = (cabi.MlpLayer * len(layers))()
+    keep = []
+    for i, (w, sc, sh) in enumerate(layers):
+        for t, nm in ((w, "weight"), (sc, "scale"), (sh, "shift")):
+            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
+        w2 = w.reshape(w.size(0), -1)
+        keep.append(w2)
+        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
+        arr[i].weight, arr[i].scale, arr[i].shift = w2.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    return arr, keep
+
+
+def interp_mlp_forward(known_feats, idx3, weight3, rel_xyz, nsample, layers, known_feats_pm=None):
+    """Fused 3-neighbour blend -> cat(rel xyz) -> SharedMLP -> max over nsample (include/b200_pointnet2.h:
+    b200pn2_interp_mlp_forward).  known_feats (B,C,m), idx3/weight3/rel_xyz (B, M*nsample, 3) -> (B, cout, M)."""
+    for t, nm in ((idx3, "idx3"), (weight3, "weight3")):
+        _contig(t, nm); _cuda(t, nm)
+    _is_int(idx3, "idx3"); _is_float(weight3, "weight3")
+    if rel_xyz is not None:
+        _contig(rel_xyz, "rel_xyz"); _is_float(rel_xyz, "rel_xyz"); _cuda(rel_xyz, "rel_xyz")
+    if known_feats is not None:
+        _contig(known_feats, "known_feats"); _is_float(known_feats, "known_feats"); _cuda(known_feats, "known_feats")
+        B, C, m = known_feats.shape
+    else:
+        _contig(known_feats_pm, "known_feats_pm"); _is_float(known_feats_pm, "known_feats_pm")
+        B, m, C = known_feats_pm.shape
+    rows = idx3.size(1)
+    _chk(rows % int(nsample) == 0, "idx3 rows must be a multiple of nsample")
+    M = rows // int(nsample)
+    arr, keep = _layer_array(layers)
+    dev = idx3.device
+    out = torch.empty((B, layers[-1][0].size(0), M), dtype=torch.float32, device=dev)
+    nbytes = 0 if known_feats_pm is not None else ((B * m * C * 4 + 255) // 256) * 256
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes else None
+    with torch.cuda.device(dev):
+        cabi.check(_L().b200pn2_interp_mlp_forward(B, m, M, int(nsample), C, _p(known_feats), _p(known_feats_pm), _p(idx3),
+                                                   _p(weight3), _p(rel_xyz), len(layers), arr, _p(out), _p(ws), nbytes,
+                                                   stream_ptr()), "interp_mlp_forward")
+    return out

@@ -197,3 +197,31 @@ class GroupAll(nn.Module):
             grouped = features.unsqueeze(2)
             new_features = torch.cat([grouped_xyz, grouped], dim=1) if self.use_xyz else grouped
         return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
+
+
+def grid_interp_mlp_max(known_feats, idx, weight, rel_xyz, nsample, shared_mlp):
+    """IoU-branch feature sampler (reference models/grid_conv_module.py:87-113): blend the three nearest seeds with
+    `weight`, prepend the relative grid coordinates, run `shared_mlp` (a pytorch_utils.SharedMLP) and max-pool over the
+    `nsample` grid points of each box.  known_feats (B,C,m), idx/weight/rel_xyz (B, K*nsample, 3) -> (B, C_out, K).
+
+    One fused tensor-core kernel when the MLP is in eval mode and no gradient is required; otherwise the same math
+    op by op (three_interpolate -> cat -> SharedMLP -> max_pool2d)."""
+    import os
+    B, C, _ = known_feats.shape
+    K = idx.shape[1] // nsample
+    need_grad = torch.is_grad_enabled() and (known_feats.requires_grad or weight.requires_grad or rel_xyz.requires_grad or
+                                             any(p.requires_grad for p in shared_mlp.parameters()))
+    layers = None
+    if not need_grad and os.environ.get("B200_SA_FUSED", "1") != "0" and hasattr(shared_mlp, "fold_affine"):
+        layers = shared_mlp.fold_affine()
+    if layers is not None and C % 4 == 0 and 128 % nsample == 0 and nsample >= 8:
+        try:
+            return _ext.interp_mlp_forward(known_feats.contiguous(), idx.contiguous(), weight.contiguous(),
+                                           rel_xyz.contiguous(), nsample, layers)
+        except RuntimeError as e:  # widths outside the tensor-core kernel's range -> generic path
+            if "not supported" not in str(e):
+                raise
+    interp = three_interpolate(known_feats, idx, weight)                                  # (B, C, K*nsample)
+    x = torch.cat([rel_xyz.transpose(1, 2).contiguous().view(B, 3, K, nsample), interp.view(B, C, K, nsample)], 1)
+    x = shared_mlp(x)
+    return torch.nn.functional.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)

@@ -188,10 +188,13 @@ class VoteNetPath(nn.Module):
         w = (1 / (dist + 1e-8)).view(B, -1, 3)
         w = (w / w.sum(2, keepdim=True)).contiguous()
         rel = whole - center[:, :, None, :].expand(-1, -1, 64, -1).reshape(B, -1, 3)
-        interp = ops.utils.three_interpolate(seed_features, idx, w)                             # (B,C,K*64)
-        x = torch.cat([rel.transpose(1, 2).contiguous().view(B, 3, K, 64), interp.view(B, feat_dim, K, 64)], 1)
-        x = self.mlp_before_iou(x)
-        x = F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+        if hasattr(ops.utils, "grid_interp_mlp_max"):     # fused sampler + MLP + max
+            x = ops.utils.grid_interp_mlp_max(seed_features, idx, w, rel.contiguous(), 64, self.mlp_before_iou)
+        else:
+            interp = ops.utils.three_interpolate(seed_features, idx, w)                         # (B,C,K*64)
+            x = torch.cat([rel.transpose(1, 2).contiguous().view(B, 3, K, 64), interp.view(B, feat_dim, K, 64)], 1)
+            x = self.mlp_before_iou(x)
+            x = F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
         net = F.relu(self.bn1_iou(self.conv1_iou(x)))
         net = F.relu(self.bn2_iou(self.conv2_iou(net)))
         return self.conv3_iou(net).transpose(2, 1)[:, :, -self.NC:]

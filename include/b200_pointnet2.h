@@ -113,6 +113,21 @@ int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int nsample, in
                        float *out_pm, int32_t *idx_out, void *workspace, size_t workspace_bytes,
                        b200_stream_t stream);
 
+/* ---- fused feature-propagation rows -> SharedMLP -> max (next-row n1 of SURVEY.md section 8f) -------------------
+ * Replaces, for the IoU branch (models/grid_conv_module.py:87-113):
+ *     three_interpolate-style blend of 3 neighbours -> cat([relative grid xyz, blended feats]) -> SharedMLP -> max over
+ *     the nsample grid points of each box
+ * Row (centre g, sample s) = [rel_xyz (3) | sum_t weight3[.,t] * known_feats[:, idx3[.,t]] (C)], q = g*nsample + s.
+ *   known_feats (B,C,m) channel-major and/or known_feats_pm (B,m,C) point-major (one may be NULL; with only the
+ *   channel-major tensor the library transposes into `workspace`, >= B*m*C*4 bytes rounded up to 256)
+ *   idx3 (B, M*nsample, 3) int32, weight3 (B, M*nsample, 3), rel_xyz (B, M*nsample, 3) or NULL (no xyz channels)
+ *   out (B, cout_last, M).  Runs on the tcgen05 kernel; widths must be multiples of 32 (hidden <= 128, last <= 128 or 256),
+ *   nsample a divisor of 128 (>= 8), C a multiple of 4.                                                               */
+int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample, int C, const float *known_feats,
+                               const float *known_feats_pm, const int32_t *idx3, const float *weight3,
+                               const float *rel_xyz, int num_layers, const b200_mlp_layer *layers, float *out,
+                               void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

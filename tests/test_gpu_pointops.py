@@ -148,3 +148,32 @@ def test_three_nn_gridconv_shape(pkg, orc):
     assert np.array_equal(idx[:1].cpu().numpy(), ridx) and np.array_equal(d2[:1].cpu().numpy(), rd2)
     d = d2.cpu().numpy()
     assert (d[..., 0] <= d[..., 1]).all() and (d[..., 1] <= d[..., 2]).all()
+
+
+@pytest.mark.parametrize("name", ["c1", "ragged", "small", "dups", "tiny", "mid"])
+def test_ball_query_grid_path_bit_exact(pkg, orc, name, monkeypatch):
+    """The hashed-grid search (ball_query_grid.cu, default for N >= 8192) forced on for every case, including radii far
+    larger than the cloud (every bucket overflows -> exact in-warp fallback) and duplicate-heavy clouds."""
+    import pointnet2._ext as ext
+    monkeypatch.setenv("B200_BQ_GRID", "1")
+    kw, npoint, radius, nsample = CASES[name]
+    xyz = cases.cloud(**kw)
+    fps = orc.furthest_point_sampling(xyz, npoint)
+    new_xyz = np.take_along_axis(xyz, fps[:, :, None].astype(np.int64), 1)
+    for r, ns in ((radius, nsample), (radius * 0.3, 4), (radius * 6, nsample), (1e-4, 3)):
+        got = ext.ball_query(dev(new_xyz), dev(xyz), r, ns).cpu().numpy()
+        assert np.array_equal(got, orc.ball_query(new_xyz, xyz, r, ns)), (name, r, ns)
+    monkeypatch.setenv("B200_BQ_GRID", "0")
+    got = ext.ball_query(dev(new_xyz), dev(xyz), radius, nsample).cpu().numpy()
+    assert np.array_equal(got, orc.ball_query(new_xyz, xyz, radius, nsample))
+
+
+def test_ball_query_grid_far_coordinates(pkg, orc, monkeypatch):
+    """Clouds far from the origin (cell indices beyond the fp32-safe range take the exact scan) and negative coordinates."""
+    import pointnet2._ext as ext
+    monkeypatch.setenv("B200_BQ_GRID", "1")
+    for shift in (-37.5, 1.0e3, 3.0e5):
+        xyz = cases.cloud(11, 2, 3000) + np.float32(shift)
+        new_xyz = xyz[:, :200].copy()
+        got = ext.ball_query(dev(new_xyz), dev(xyz), 0.25, 16).cpu().numpy()
+        assert np.array_equal(got, orc.ball_query(new_xyz, xyz, 0.25, 16)), shift

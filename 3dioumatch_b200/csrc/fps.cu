@@ -456,7 +456,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       const int warps_per_sched = th >= 128 ? th / 128 : 1;
       const bool ties = ((cs * th) % bs) != 0;
       const double iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
-                          (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 60.0 : 0.0);
+                          (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 260.0 : 0.0);  // >8: non-portable size; also keeps half the SMs free for the feature kernels
       const double cost = waves * iter;
       if (cost < best_cost) {
         best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th;

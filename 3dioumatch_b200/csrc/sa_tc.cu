@@ -52,6 +52,12 @@ struct TcParams {
   int vec_gather;  // feature rows are 16-byte aligned runs of a multiple of 4 floats
   // mode 1 (feature-propagation style rows, models/grid_conv_module.py:87-108): row (centre g, sample s) is the
   // inverse-distance blend of three source rows, channels [rel xyz (3) | sum_t w_t * feat[idx_t] (C)]
+  // shared-memory / TMEM geometry chosen by the launcher
+  int r1_bytes;      // activation region: layer-1 A stages, later X_hi | X_lo
+  int x_lo_off;      // byte offset of X_lo inside R1 (= hidden k-blocks * 16 KB)
+  int wslot_bytes;   // size of one weight stage slot in R2
+  int small_off;     // TMEM column offset of the correction-term accumulators (128 or 256)
+  int compact;       // 1: the final epilogue's slab aliases R2 (all MMAs finished first) -> ~105 KB, 2 CTAs per SM
   int mode;
   const int32_t *idx3;   // (B, M*ns, 3)
   const float *w3;       // (B, M*ns, 3)
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
     const int chunk = it & 7, row = (it >> 3) % rows, rest = (it >> 3) / rows;
     const int kb = rest % p.nkb[l], half = rest / p.nkb[l];
-    const int n = half * 128 + row;
+    const int n = half * rows + row;
     float v[4], hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -108,15 +114,17 @@ __device__ unsigned long long g_tc_prof[16];
 #endif
 
 // ---- the fused kernel -----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) {
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *R1 = base;                       // 128 KB
-  uint8_t *R2 = base + 8 * TC_KB_BYTES;     // 2 x 32 KB
-  float *s_scale = reinterpret_cast<float *>(R2 + 2 * TC_WSTAGE_BYTES);  // [TC_MAXL][256]
+  uint8_t *R1 = base;                       // p.r1_bytes
+  uint8_t *R2 = base + p.r1_bytes;          // 2 x p.wslot_bytes
+  float *s_scale = reinterpret_cast<float *>(R2 + 2 * p.wslot_bytes);  // [TC_MAXL][256]
   float *s_shift = s_scale + TC_MAXL * 256;
-  float *s_slab = s_shift + TC_MAXL * 256;  // [128][36] transpose slab of the final epilogue (its own region: the
-                                            // epilogue of half 0 runs while half 1's MMAs still read R1 and R2)
+  // [128][36] transpose slab of the final epilogue.  Normally its own region (the epilogue of half 0 runs while half
+  // 1's MMAs still read R1 and R2); in compact mode it aliases R2 and the epilogue starts after the last MMA.
+  float *s_slab = p.compact ? reinterpret_cast<float *>(R2) : s_shift + TC_MAXL * 256;
 
   __shared__ uint64_t full_a[2], empty_a[2], full_w[2], empty_w[2], accum_full, x_ready, accum_half[2];
   __shared__ uint32_t tmem_base_s;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
   const int g_here = min(p.G, p.M - m0);
   const int nl = p.nl;
 
-  if (warp == 4) tc::tmem_alloc<512>(&tmem_base_s);
+  if (warp == 4) tc::tmem_alloc<TMEM_COLS>(&tmem_base_s);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&full_a[s], 128);
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
           const int st = i & 1;
           tc::mbar_wait(&empty_w[st], (uint32_t)(((i >> 1) & 1) ^ 1));
           tc::mbar_arrive_expect_tx(&full_w[st], stage_bytes);
-          tc::bulk_g2s(R2 + st * TC_WSTAGE_BYTES, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
+          tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
         }
       }
     }
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
         const uint32_t idesc = tc::make_idesc_tf32(128, p.L[l].rows);
         const uint32_t wlo_off = (uint32_t)p.L[l].rows * 128u;
         for (int h = 0; h < p.L[l].nhalf; ++h) {
-          const uint32_t d_addr = tmem_d + (uint32_t)(h * 128);
+          const uint32_t d_addr = tmem_d + (uint32_t)(h * p.L[l].rows);
           for (int kb = 0; kb < nkb; ++kb, ++i) {
             const int ws = i & 1;
             uint32_t a_hi, a_lo;
@@ -196,19 +204,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
               a_lo = a_hi + TC_KB_BYTES;
             } else {
               a_hi = tc::smem_addr(R1 + kb * TC_KB_BYTES);
-              a_lo = a_hi + 4 * TC_KB_BYTES;
+              a_lo = a_hi + (uint32_t)p.x_lo_off;
             }
             tc::mbar_wait(&full_w[ws], (uint32_t)((i >> 1) & 1));
             tc::tc_fence_after_sync();
-            const uint32_t w_hi = tc::smem_addr(R2 + ws * TC_WSTAGE_BYTES), w_lo = w_hi + wlo_off;
+            const uint32_t w_hi = tc::smem_addr(R2 + ws * p.wslot_bytes), w_lo = w_hi + wlo_off;
             const uint64_t da_hi = tc::make_desc_sw128(a_hi), da_lo = tc::make_desc_sw128(a_lo);
             const uint64_t dw_hi = tc::make_desc_sw128(w_hi), dw_lo = tc::make_desc_sw128(w_lo);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
               tc::mma_tf32(d_addr, da_hi + adv, dw_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-              tc::mma_tf32(d_addr + 256u, da_lo + adv, dw_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-              tc::mma_tf32(d_addr + 256u, da_hi + adv, dw_lo + adv, idesc, 1u);
+              tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_lo + adv, dw_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+              tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_hi + adv, dw_lo + adv, idesc, 1u);
             }
             if (l == 0) tc::mma_commit(&empty_a[kb & 1]);
             tc::mma_commit(&empty_w[ws]);
@@ -335,10 +343,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
       const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
       if (l + 1 < nl) {
         // hidden layer: X = relu(scale*acc+shift) -> split -> R1 as the next layer's K-major operand
-        uint8_t *x_hi = R1, *x_lo = R1 + 4 * TC_KB_BYTES;
+        uint8_t *x_hi = R1, *x_lo = R1 + p.x_lo_off;
+        const uint32_t small = (uint32_t)p.small_off;
         uint32_t ra[32], ra2[32], rb[32], rb2[32];
         tc::tmem_ld_32x32(lane_addr, ra);
-        tc::tmem_ld_32x32(lane_addr + 256u, ra2);
+        tc::tmem_ld_32x32(lane_addr + small, ra2);
         auto emit = [&](int c0, const uint32_t (&r)[32], const uint32_t (&r2)[32]) {
           uint8_t *kb_hi = x_hi + (c0 >> 5) * TC_KB_BYTES, *kb_lo = x_lo + (c0 >> 5) * TC_KB_BYTES;
 #pragma unroll
@@ -363,14 +372,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
           tc::tmem_ld_wait();  // ra ready
           if (c0 + 32 < H) {
             tc::tmem_ld_32x32(lane_addr + (uint32_t)(c0 + 32), rb);
-            tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)(c0 + 32), rb2);
+            tc::tmem_ld_32x32(lane_addr + small + (uint32_t)(c0 + 32), rb2);
           }
           emit(c0, ra, ra2);
           if (c0 + 32 < H) {
             tc::tmem_ld_wait();  // rb ready
             if (c0 + 64 < H) {
               tc::tmem_ld_32x32(lane_addr + (uint32_t)(c0 + 64), ra);
-              tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)(c0 + 64), ra2);
+              tc::tmem_ld_32x32(lane_addr + small + (uint32_t)(c0 + 64), ra2);
             }
             emit(c0 + 32, rb, rb2);
           }
@@ -386,14 +395,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
         float *slab = s_slab;  // pitch 36 floats: conflict-free STS.128 / LDS
         constexpr int PITCH = 36;
         const int G = p.G;                             // centres per tile (128 / ns)
+        const int rows_l = p.L[l].rows;
+        if (p.compact) {  // the slab aliases the weight stages: every MMA must be done
+          tc::mbar_wait(&accum_half[p.L[l].nhalf - 1], 0u);
+          tc::tc_fence_after_sync();
+        }
         for (int c0 = 0; c0 < cout; c0 += 32) {
-          if ((c0 & 127) == 0) {
-            tc::mbar_wait(&accum_half[c0 >> 7], 0u);
+          if (!p.compact && (c0 % rows_l) == 0) {
+            tc::mbar_wait(&accum_half[c0 / rows_l], 0u);
             tc::tc_fence_after_sync();
           }
           uint32_t r[32], r2[32];
           tc::tmem_ld_32x32(lane_addr + (uint32_t)c0, r);
-          tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)c0, r2);
+          tc::tmem_ld_32x32(lane_addr + (uint32_t)p.small_off + (uint32_t)c0, r2);
           tc::tmem_ld_wait();
           asm volatile("bar.sync 1, 128;" ::: "memory");  // previous slab fully consumed
 #pragma unroll
@@ -440,7 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sa_tc_kernel(const TcParams p) 
 #endif
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc<512>(tmem_d);
+  if (warp == 4) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
 #ifdef B200_TC_PROFILE
@@ -488,20 +502,46 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   p.inv_r = normalize_xyz ? (float)(1.0 / (double)radius) : 1.0f;
   p.xyz = xyz; p.feat_pm = feat_pm; p.new_xyz = new_xyz; p.idx = idx; p.out = out; p.out_pm = out_pm;
   p.vec_gather = (C > 0 && (C & 3) == 0 && ((((uintptr_t)feat_pm) & 15) == 0)) ? 1 : 0;
+  // ---- geometry: rows per weight stage, shared-memory regions, TMEM columns ---------------------------------------
+  const int cout_last = layers[num_layers - 1].cout;
+  int hid_max = 0;
+  for (int l = 0; l + 1 < num_layers; ++l) hid_max = layers[l].cout > hid_max ? layers[l].cout : hid_max;
+  const int nkb1 = (layers[0].cin + 31) / 32, nkbh = hid_max / 32;
+  const int a_stages = nkb1 < 2 ? nkb1 : 2;
+  int r1 = a_stages * 2 * (int)TC_KB_BYTES;
+  if (2 * nkbh * (int)TC_KB_BYTES > r1) r1 = 2 * nkbh * (int)TC_KB_BYTES;
+  // compact variant: last layer streamed as 64-row halves, slab aliased on the weight stages, 256 TMEM columns
+  auto slot_for = [&](int last_rows) {
+    int mx = last_rows;
+    for (int l = 0; l + 1 < num_layers; ++l) mx = layers[l].cout > mx ? layers[l].cout : mx;
+    return mx * 256;
+  };
+  const bool can_compact = cout_last == 128 && hid_max <= 128;
+  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float);
+  const size_t smem_compact = fixed + (size_t)r1 + 2 * (size_t)slot_for(64);
+  const bool compact = can_compact && smem_compact <= 110 * 1024;
+  const int last_rows = compact ? 64 : (cout_last <= 128 ? cout_last : 128);
+  if (cout_last > 128 && cout_last != 256) {
+    set_error("sa_forward(tc): last-layer width %d unsupported", cout_last);
+    return 1;
+  }
+  p.r1_bytes = r1;
+  p.x_lo_off = nkbh * (int)TC_KB_BYTES;
+  p.wslot_bytes = slot_for(last_rows);
+  p.compact = compact ? 1 : 0;
+  p.small_off = (cout_last > 128) ? 256 : 128;
+  const size_t smem = compact ? smem_compact
+                              : fixed + (size_t)r1 + 2 * (size_t)p.wslot_bytes + 128 * 36 * sizeof(float);
   size_t off = 0;
   pk.nl = num_layers;
   pk.perm_c = use_xyz ? C : -1;
   for (int l = 0; l < num_layers; ++l) {
     TcLayer &t = p.L[l];
+    const bool last = l == num_layers - 1;
     t.scale = layers[l].scale; t.shift = layers[l].shift; t.cin = layers[l].cin; t.cout = layers[l].cout;
     t.nkb = (layers[l].cin + 31) / 32;
-    t.nhalf = (layers[l].cout + 127) / 128;
-    // rows per stage: the whole layer when it fits one MMA (<= 128), else two equal halves of 128
-    t.rows = layers[l].cout <= 128 ? layers[l].cout : 128;
-    if (layers[l].cout > 128 && layers[l].cout != 256) {
-      set_error("sa_forward(tc): last-layer width %d unsupported", layers[l].cout);
-      return 1;
-    }
+    t.rows = last ? last_rows : layers[l].cout;
+    t.nhalf = layers[l].cout / t.rows;
     t.packed_off = off;
     pk.w[l] = layers[l].weight; pk.cin[l] = t.cin; pk.cout[l] = t.cout; pk.nkb[l] = t.nkb; pk.nhalf[l] = t.nhalf;
     pk.rows[l] = t.rows;
@@ -513,15 +553,21 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
-  const size_t smem = 1024 + 8 * TC_KB_BYTES + 2 * TC_WSTAGE_BYTES + 2 * TC_MAXL * 256 * sizeof(float) +
-                      128 * 36 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static size_t attr256 = 0, attr512 = 0;
   dim3 grid(ceil_div(M, p.G), B);
-  sa_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  if (p.small_off == 128) {
+    if (smem > attr256) {
+      B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr256 = smem;
+    }
+    sa_tc_kernel<256><<<grid, TC_THREADS, smem, stream>>>(p);
+  } else {
+    if (smem > attr512) {
+      B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr512 = smem;
+    }
+    sa_tc_kernel<512><<<grid, TC_THREADS, smem, stream>>>(p);
+  }
   B200_LAUNCH_OK("sa_tc_kernel");
   B200_CUDA_OK(cudaFreeAsync(packed, stream));
   return 0;

@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--lanes", type=int, default=3,
                     help="consecutive steps alternate between this many CUDA streams (software pipelining across steps)")
     ap.add_argument("--no-prefetch", action="store_true", help="do not run the FPS index chain on a side stream")
+    ap.add_argument("--graphs", type=int, default=-1,
+                    help="replay each lane's step from a CUDA graph (default: on for --impl b200; the reference launches on "
+                         "the legacy default stream and cannot be captured)")
     ap.add_argument("--batch", type=int, default=B_SCENES)
     ap.add_argument("--points", type=int, default=N_POINTS)
     return ap.parse_args()
@@ -246,8 +249,39 @@ def main():
     out_keys = ("iou_labels", "iou_scores", "center", "size", "heading", "objectness")
     cabi = importlib.import_module("3dioumatch_b200._cabi") if a.impl == "b200" else None
 
+    # ---- CUDA graphs: one captured step per lane (static input/output buffers), replayed with fresh inputs ----------
+    use_graphs = (a.graphs == 1) or (a.graphs == -1 and a.impl == "b200")
+    graphs = []
+    if use_graphs:
+        try:
+            with torch.no_grad():
+                for lane in lanes:
+                    static_pc = torch.empty_like(dev_pcs[0])
+                    static_pc.copy_(dev_pcs[0])
+                    static_gt = dev_gt.clone()
+                    with torch.cuda.stream(lane):
+                        for _ in range(3):
+                            net(static_pc, static_gt)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=lane):
+                        static_out = net(static_pc, static_gt)
+                    graphs.append((g, static_pc, static_out, static_gt))
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001 -- a failed capture must not hide the eager measurement
+            print("bench.py: CUDA-graph capture failed (%s); running eagerly" % (str(e).splitlines()[0][:200]),
+                  file=sys.stderr)
+            graphs, use_graphs = [], False
+            torch.cuda.synchronize()
+
     def step_resident(i):
-        with torch.cuda.stream(lanes[i % len(lanes)]):
+        lane = i % len(lanes)
+        with torch.cuda.stream(lanes[lane]):
+            if use_graphs:
+                g, static_pc, static_out, _ = graphs[lane]
+                static_pc.copy_(dev_pcs[i % N_ROTATE], non_blocking=True)
+                g.replay()
+                return static_out
             return net(dev_pcs[i % N_ROTATE], dev_gt)
 
     host_out = [dict() for _ in lanes]
@@ -255,9 +289,15 @@ def main():
     def step_e2e(i):
         lane = i % len(lanes)
         with torch.cuda.stream(lanes[lane]):
-            pc = host_pcs[i % N_ROTATE].to(dev, non_blocking=True)
-            gt = host_gt.to(dev, non_blocking=True)
-            res = net(pc, gt)
+            if use_graphs:
+                g, static_pc, res, static_gt = graphs[lane]
+                static_pc.copy_(host_pcs[i % N_ROTATE], non_blocking=True)   # H2D from pinned memory
+                static_gt.copy_(host_gt, non_blocking=True)
+                g.replay()
+            else:
+                pc = host_pcs[i % N_ROTATE].to(dev, non_blocking=True)
+                gt = host_gt.to(dev, non_blocking=True)
+                res = net(pc, gt)
             for k in out_keys:
                 if k not in host_out[lane]:
                     host_out[lane][k] = torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True)
@@ -276,8 +316,10 @@ def main():
         e0.record(cur)
         for s_ in lanes:
             s_.wait_stream(cur)          # every lane starts after the start event
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
+        timed.enqueue_ms = (time.perf_counter() - t_host) * 1e3 / steps
         for s_ in lanes:
             cur.wait_stream(s_)          # the stop event waits for all lanes (and their side streams)
         e1.record(cur)
@@ -290,6 +332,13 @@ def main():
         barrier()
         return ms
 
+    launches_per_step = 0
+    if cabi:
+        with torch.no_grad():
+            c0 = cabi.launch_count()
+            net(dev_pcs[0], dev_gt)          # one eager step: how many libb200pc kernels a step launches
+            torch.cuda.synchronize()
+            launches_per_step = cabi.launch_count() - c0
     with torch.no_grad():
         for i in range(max(a.warmup, 3)):
             step_resident(i)
@@ -298,7 +347,10 @@ def main():
         sampler.start()
         launches0 = cabi.launch_count() if cabi else 0
         ms_res = timed(step_resident, a.steps)
+        enqueue_ms = timed.enqueue_ms
         launches = (cabi.launch_count() - launches0) if cabi else 0
+        if use_graphs:
+            launches = launches_per_step * a.steps   # replayed from the captured graphs (not re-counted by the library)
         ms_e2e = timed(step_e2e, a.steps)
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -316,7 +368,8 @@ def main():
         "impl": a.impl,
         "config": {"workload": "configs[1]: ScanNet-shaped synthetic (B=%d,N=%d,C=4) VoteNet-IoU-branch forward dataflow, "
                                "%d proposals, IoU labels vs %d GT slots; random-init weights, eval-mode BN" % (B, N, N_PROPOSAL, N_GT),
-                   "scenes_per_gpu_per_step": B, "lanes": len(lanes),
+                   "scenes_per_gpu_per_step": B, "lanes": len(lanes), "cuda_graphs": bool(use_graphs),
+                   "host_enqueue_ms_per_step": round(enqueue_ms, 3),
                    "prefetch_fps_chain": bool(net.backbone.prefetch), "parallelism": "scene-sharded x%d, no data-path collective" % n_gpus,
                    "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (N_ROTATE, N_ROTATE * B * N * 16 / 1e6),
                    "tf32": "torch defaults (cudnn conv TF32 allowed) for the torch-side 1x1 convs; all libb200pc kernels fp32"},

@@ -58,6 +58,7 @@ struct TcParams {
   int wslot_bytes;   // size of one weight stage slot in R2
   int small_off;     // TMEM column offset of the correction-term accumulators (128 or 256)
   int compact;       // 1: the final epilogue's slab aliases R2 (all MMAs finished first) -> ~105 KB, 2 CTAs per SM
+  int cluster;       // 2: CTA pairs share every weight stage through one multicast bulk copy (half the L2 reads)
   int mode;
   const int32_t *idx3;   // (B, M*ns, 3)
   const float *w3;       // (B, M*ns, 3)
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
   float *s_slab = p.compact ? reinterpret_cast<float *>(R2) : s_shift + TC_MAXL * 256;
 
   __shared__ uint64_t full_a[2], empty_a[2], full_w[2], empty_w[2], accum_full, x_ready, accum_half[2];
+  __shared__ uint64_t empty_w_peer[2];  // rank 0 only: the peer CTA has finished reading weight stage s
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
       tc::mbar_init(&empty_a[s], 1);
       tc::mbar_init(&full_w[s], 1);
       tc::mbar_init(&empty_w[s], 1);
+      tc::mbar_init(&empty_w_peer[s], 1);
     }
     tc::mbar_init(&accum_full, 1);
     tc::mbar_init(&accum_half[0], 1);
@@ -159,6 +162,9 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
+  const bool paired = p.cluster == 2;
+  const uint32_t crank = paired ? tc::cluster_ctarank() : 0u;
+  if (paired) tc::cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
 
   const int nkb1 = p.L[0].nkb;
 
@@ -174,7 +180,14 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
           const int st = i & 1;
           tc::mbar_wait(&empty_w[st], (uint32_t)(((i >> 1) & 1) ^ 1));
           tc::mbar_arrive_expect_tx(&full_w[st], stage_bytes);
-          tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
+          if (!paired) {
+            tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
+          } else if (crank == 0) {
+            // one L2 read feeds both CTAs of the pair; the slot must be free in the peer as well
+            tc::mbar_wait(&empty_w_peer[st], (uint32_t)(((i >> 1) & 1) ^ 1));
+            tc::bulk_g2s_multicast(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st],
+                                   (uint16_t)0x3);
+          }
         }
       }
     }
@@ -220,6 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
             }
             if (l == 0) tc::mma_commit(&empty_a[kb & 1]);
             tc::mma_commit(&empty_w[ws]);
+            if (paired && crank == 1) tc::mma_commit_multicast(&empty_w_peer[ws], (uint16_t)0x1);  // tell rank 0
           }
           if (l == nl - 1) tc::mma_commit(&accum_half[h]);  // the final epilogue of half h overlaps half h+1's MMAs
         }
@@ -454,6 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
 #endif
   tc::tc_fence_before_sync();
   __syncthreads();
+  if (paired) tc::cluster_sync_all();  // no CTA leaves while its peer may still signal / multicast into it
   if (warp == 4) tc::tmem_dealloc<TMEM_COLS>(tmem_d);
 }
 
@@ -554,19 +569,36 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
   static size_t attr256 = 0, attr512 = 0;
-  dim3 grid(ceil_div(M, p.G), B);
+  // weight-bound (one CTA per SM) shapes run as CTA pairs sharing each weight stage (B200_SA_TC_PAIR=0 disables)
+  const char *pe = getenv("B200_SA_TC_PAIR");
+  const bool pair = !compact && !(pe && atoi(pe) == 0);
+  p.cluster = pair ? 2 : 1;
+  int tiles = ceil_div(M, p.G);
+  if (pair) tiles = (tiles + 1) & ~1;  // the padding CTA runs the pipeline on zero rows
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, B, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = pair ? 2 : 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   if (p.small_off == 128) {
     if (smem > attr256) {
       B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr256 = smem;
     }
-    sa_tc_kernel<256><<<grid, TC_THREADS, smem, stream>>>(p);
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, sa_tc_kernel<256>, p));
   } else {
     if (smem > attr512) {
       B200_CUDA_OK(cudaFuncSetAttribute(sa_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr512 = smem;
     }
-    sa_tc_kernel<512><<<grid, TC_THREADS, smem, stream>>>(p);
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, sa_tc_kernel<512>, p));
   }
   B200_LAUNCH_OK("sa_tc_kernel");
   B200_CUDA_OK(cudaFreeAsync(packed, stream));

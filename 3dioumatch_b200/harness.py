@@ -132,6 +132,7 @@ class VoteNetPath(nn.Module):
                  num_proposal=256, mean_size_seed=0):
         super().__init__()
         self.ops = ops
+        self.block_diagonal_iou = True   # use the batched block-diagonal IoU entry when the stack offers it
         self.K, self.NH, self.NS, self.NC = num_proposal, num_heading_bin, num_size_cluster, num_class
         rng = np.random.default_rng(mean_size_seed)
         self.register_buffer("mean_size", torch.from_numpy((rng.random((num_size_cluster, 3)) + 0.3).astype(np.float32)))
@@ -219,6 +220,14 @@ class VoteNetPath(nn.Module):
         B, K, G = center.shape[0], self.K, gt_boxes.shape[1]
         pred = torch.cat([center, size * 2, -heading[..., None]], 2)
         pa, pb = pred.view(-1, 7).contiguous(), gt_boxes.reshape(-1, 7).contiguous()
+        if hasattr(ops.iou, "boxes_iou3d_batched") and self.block_diagonal_iou:
+            # only the per-scene diagonal blocks of the all-pairs matrix are ever consumed
+            # (loss_helper_iou.py:107-109) -> evaluate exactly those (B, K, G) pairs in one launch
+            blk = ops.iou.boxes_iou3d_batched(pred.contiguous(), gt_boxes.contiguous())
+            iou_labels, assignment = blk.max(dim=2)
+            return dict(seed_xyz=seed_xyz, seed_inds=seed_inds, vote_xyz=vote_xyz, aggregated_vote_inds=sample_inds,
+                        center=center, size=size, heading=heading, objectness=objectness, iou_scores=iou_scores,
+                        iou_labels=iou_labels, object_assignment=assignment, pred_bbox=pred)
         if ops.name == "reference":
             # the reference launches its IoU kernel on the LEGACY default stream (iou3d_nms_kernel.cu:396); when the
             # harness runs on a non-blocking stream that launch must be ordered by hand

@@ -28,8 +28,8 @@ N_ROTATE = 32  # distinct input batches cycled through the timed region: 32 x 5.
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref", action="store_true", help="skip the in-run timing of the reference CUDA ops")
@@ -46,37 +46,82 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in-process every 20 ms (nvidia-smi every 200 ms
+    as the fallback; B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.stop_flag = gpu_index, False
+        self.sm, self.max_sm, self.reasons, self.power = [], None, set(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the torch device to its NVML handle through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+            self.handle = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+        except Exception:
+            pass
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [c.strip() for c in line.split(",")]
+            if len(r) > 7:
+                self.sm.append(float(r[1]))
+                self.max_sm = float(r[2])
+                for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                                  ("sw_power_cap", 7)):
+                    if r[col].lower().startswith("active"):
+                        self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml else 0.2)
 
     def summary(self):
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
-                              ("sw_power_cap", 7)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.max_sm) if self.max_sm else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "power_w_max": round(max(self.power), 1) if self.power else None,
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def load_stack(impl):
@@ -395,12 +440,46 @@ def main():
             top = max(ours, key=lambda k: ours[k]["ms"] * max(ours[k]["calls_per_step"], 1))
             t = ours[top]
             ach = t["alg_bytes"] / (t["ms"] / 1e3) / 1e9
+            traffic = None
+            try:  # DRAM bytes per launch of the same kernel/shape from the committed `ncu --set full` capture
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+                traffic = tr.get(top, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
             line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": round(ach, 3), "peak": hbm_peak,
-                                "unit": "GB/s", "frac": round(ach / hbm_peak, 5), "traffic": None,
+                                "unit": "GB/s", "frac": round(ach / hbm_peak, 5), "traffic": traffic,
                                 "peak_source": peak_src, "launch_ms": t["ms"],
                                 "achieved_fp32_tflops": round(t["alg_flops"] / (t["ms"] / 1e3) / 1e12, 3),
                                 "note": "algorithmic bytes / launch time; this kernel is latency/FP32-bound, not HBM-bound "
                                         "(DESIGN.md section 4)"}
+        # ---- configs[2]: 256 x 256 rotated 3D IoU + NMS (device-resident boxes, CUDA events) ------------------------
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import cases
+            ba = torch.from_numpy(cases.boxes(0, 256)).to(dev)
+            bb = torch.from_numpy(cases.boxes(1, 256, jitter_of=cases.boxes(0, 256))).to(dev)
+            sc = torch.rand(256, device=dev)
+
+            def c3_time(fn, iters=20):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / iters * 1e3
+            line["c3"] = {"workload": "configs[2]: boxes_iou3d_gpu 256x256 + nms_gpu(256 boxes, thresh 0.25)",
+                          "iou3d_us": round(c3_time(lambda: ops.iou.boxes_iou3d_gpu(ba, bb)), 2)}
+            try:
+                line["c3"]["nms_us"] = round(c3_time(lambda: ops.iou.nms_gpu(ba, sc, 0.25)), 2)
+            except Exception as e:  # the reference's nms_gpu passes a LongTensor to an int32 reader
+                line["c3"]["nms_us"] = None
+                line["c3"]["nms_error"] = str(e).splitlines()[0][:120]
+        except Exception as e:  # noqa: BLE001
+            line["c3"] = {"error": str(e)[:200]}
         if a.impl == "reference":
             line["cpu_baseline"] = {"value": line["value"], "unit": "scenes/s", "kind": "reference",
                                     "cores": os.cpu_count(),
@@ -419,6 +498,7 @@ def main():
                                    env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
                 line["reference_cuda"] = {"value": ref.get("value"), "e2e": ref.get("e2e", {}).get("value"),
+                                          "c3": ref.get("c3"),
                                           "ms_per_step": ref.get("ms_per_step"), "unit": "scenes/s",
                                           "what": "unmodified reference pointnet2/_ext + iou3d_nms CUDA ops on the same GPU, same dataflow"}
                 if ref.get("value"):

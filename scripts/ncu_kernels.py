@@ -20,10 +20,14 @@ for it in range(3):
     i2 = ext.furthest_point_sampling(x1, 1024)
     x2 = ext.gather_points(x1.transpose(1, 2).contiguous(), i2).transpose(1, 2).contiguous()
     f2, _, _ = ext.sa_forward(x1, f1, x2, 0.4, 32, layers([131, 128, 128, 256]), normalize_xyz=True)
+    i3 = ext.furthest_point_sampling(x2, 512)
+    x3 = ext.gather_points(x2.transpose(1, 2).contiguous(), i3).transpose(1, 2).contiguous()
+    f3, _, _ = ext.sa_forward(x2, f2, x3, 0.8, 16, layers([259, 128, 128, 256]), normalize_xyz=True)
     grid = torch.rand(B, 256 * 64, 3, device="cuda") * 6 - 3
     d2, idx = ext.three_nn(grid, x2)
     w = torch.full((B, 256 * 64, 3), 1 / 3, device="cuda")
     ext.three_interpolate(f2, idx, w)
+    ext.interp_mlp_forward(f2, idx, w, torch.zeros_like(grid), 64, layers([259, 128, 128, 128]))
     a = torch.from_numpy(cases.boxes(0, 2048)).cuda(); b = torch.from_numpy(cases.boxes(1, 512, jitter_of=cases.boxes(0, 2048)[:512])).cuda()
     iu.boxes_iou3d_gpu(a, b)
 torch.cuda.synchronize()

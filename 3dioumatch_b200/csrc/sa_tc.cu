@@ -120,15 +120,17 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *R1 = base;                       // p.r1_bytes
-  uint8_t *R2 = base + p.r1_bytes;          // 2 x p.wslot_bytes
-  float *s_scale = reinterpret_cast<float *>(R2 + 2 * p.wslot_bytes);  // [TC_MAXL][256]
+  uint8_t *R2 = base + p.r1_bytes;          // 4 x p.wslot_bytes (one W_hi or W_lo k-block each)
+  float *s_scale = reinterpret_cast<float *>(R2 + 4 * p.wslot_bytes);  // [TC_MAXL][256]
   float *s_shift = s_scale + TC_MAXL * 256;
   // [128][36] transpose slab of the final epilogue.  Normally its own region (the epilogue of half 0 runs while half
   // 1's MMAs still read R1 and R2); in compact mode it aliases R2 and the epilogue starts after the last MMA.
   float *s_slab = p.compact ? reinterpret_cast<float *>(R2) : s_shift + TC_MAXL * 256;
 
-  __shared__ uint64_t full_a[2], empty_a[2], full_w[2], empty_w[2], accum_full, x_ready, accum_half[2];
-  __shared__ uint64_t empty_w_peer[2];  // rank 0 only: the peer CTA has finished reading weight stage s
+  // weight ring: 4 slots of one operand half-stage each (W_hi or W_lo of a k-block).  More, smaller copies in flight
+  // cover the L2 latency better than 2 x 32 KB (the stream was latency x bytes-in-flight bound at ~26 B/cycle/SM).
+  __shared__ uint64_t full_a[2], empty_a[2], full_w[4], empty_w[4], accum_full, x_ready, accum_half[2];
+  __shared__ uint64_t empty_w_peer[4];  // rank 0 only: the peer CTA has finished reading weight slot s
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&full_a[s], 128);
       tc::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       tc::mbar_init(&full_w[s], 1);
       tc::mbar_init(&empty_w[s], 1);
       tc::mbar_init(&empty_w_peer[s], 1);
@@ -175,17 +179,18 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
       for (int l = 0; l < nl; ++l) {
         const int nst = p.L[l].nhalf * p.L[l].nkb;
         const uint8_t *src = p.packed + p.L[l].packed_off;
-        const uint32_t stage_bytes = (uint32_t)p.L[l].rows * 256u;
-        for (int s = 0; s < nst; ++s, ++i) {
-          const int st = i & 1;
-          tc::mbar_wait(&empty_w[st], (uint32_t)(((i >> 1) & 1) ^ 1));
-          tc::mbar_arrive_expect_tx(&full_w[st], stage_bytes);
+        const uint32_t part_bytes = (uint32_t)p.L[l].rows * 128u;  // W_hi or W_lo of one k-block
+        for (int s = 0; s < 2 * nst; ++s, ++i) {                  // packed order: hi(0), lo(0), hi(1), lo(1), ...
+          const int st = i & 3;
+          const uint32_t par = (uint32_t)(((i >> 2) & 1) ^ 1);
+          tc::mbar_wait(&empty_w[st], par);
+          tc::mbar_arrive_expect_tx(&full_w[st], part_bytes);
           if (!paired) {
-            tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st]);
+            tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * part_bytes, part_bytes, &full_w[st]);
           } else if (crank == 0) {
             // one L2 read feeds both CTAs of the pair; the slot must be free in the peer as well
-            tc::mbar_wait(&empty_w_peer[st], (uint32_t)(((i >> 1) & 1) ^ 1));
-            tc::bulk_g2s_multicast(R2 + st * p.wslot_bytes, src + (size_t)s * stage_bytes, stage_bytes, &full_w[st],
+            tc::mbar_wait(&empty_w_peer[st], par);
+            tc::bulk_g2s_multicast(R2 + st * p.wslot_bytes, src + (size_t)s * part_bytes, part_bytes, &full_w[st],
                                    (uint16_t)0x3);
           }
         }
@@ -204,11 +209,9 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
         }
         const int nkb = p.L[l].nkb;
         const uint32_t idesc = tc::make_idesc_tf32(128, p.L[l].rows);
-        const uint32_t wlo_off = (uint32_t)p.L[l].rows * 128u;
         for (int h = 0; h < p.L[l].nhalf; ++h) {
           const uint32_t d_addr = tmem_d + (uint32_t)(h * p.L[l].rows);
-          for (int kb = 0; kb < nkb; ++kb, ++i) {
-            const int ws = i & 1;
+          for (int kb = 0; kb < nkb; ++kb, ++i) {  // i advances twice per k-block (W_hi slot, W_lo slot)
             uint32_t a_hi, a_lo;
             if (l == 0) {
               const int as = kb & 1;
@@ -219,21 +222,38 @@ __global__ void __launch_bounds__(TC_THREADS) sa_tc_kernel(const TcParams p) {
               a_hi = tc::smem_addr(R1 + kb * TC_KB_BYTES);
               a_lo = a_hi + (uint32_t)p.x_lo_off;
             }
-            tc::mbar_wait(&full_w[ws], (uint32_t)((i >> 1) & 1));
-            tc::tc_fence_after_sync();
-            const uint32_t w_hi = tc::smem_addr(R2 + ws * p.wslot_bytes), w_lo = w_hi + wlo_off;
             const uint64_t da_hi = tc::make_desc_sw128(a_hi), da_lo = tc::make_desc_sw128(a_lo);
-            const uint64_t dw_hi = tc::make_desc_sw128(w_hi), dw_lo = tc::make_desc_sw128(w_lo);
+            // --- W_hi slot: A_hi*W_hi -> big accumulator, A_lo*W_hi -> small accumulator ---
+            {
+              const int sl = i & 3;
+              tc::mbar_wait(&full_w[sl], (uint32_t)((i >> 2) & 1));
+              tc::tc_fence_after_sync();
+              const uint64_t dw = tc::make_desc_sw128(tc::smem_addr(R2 + sl * p.wslot_bytes));
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
-              tc::mma_tf32(d_addr, da_hi + adv, dw_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-              tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_lo + adv, dw_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-              tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_hi + adv, dw_lo + adv, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
+                tc::mma_tf32(d_addr, da_hi + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_lo + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+              }
+              tc::mma_commit(&empty_w[sl]);
+              if (paired && crank == 1) tc::mma_commit_multicast(&empty_w_peer[sl], (uint16_t)0x1);  // tell rank 0
             }
-            if (l == 0) tc::mma_commit(&empty_a[kb & 1]);
-            tc::mma_commit(&empty_w[ws]);
-            if (paired && crank == 1) tc::mma_commit_multicast(&empty_w_peer[ws], (uint16_t)0x1);  // tell rank 0
+            ++i;
+            // --- W_lo slot: A_hi*W_lo -> small accumulator ---
+            {
+              const int sl = i & 3;
+              tc::mbar_wait(&full_w[sl], (uint32_t)((i >> 2) & 1));
+              tc::tc_fence_after_sync();
+              const uint64_t dw = tc::make_desc_sw128(tc::smem_addr(R2 + sl * p.wslot_bytes));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                tc::mma_tf32(d_addr + (uint32_t)p.small_off, da_hi + adv, dw + adv, idesc, 1u);
+              }
+              if (l == 0) tc::mma_commit(&empty_a[kb & 1]);
+              tc::mma_commit(&empty_w[sl]);
+              if (paired && crank == 1) tc::mma_commit_multicast(&empty_w_peer[sl], (uint16_t)0x1);
+            }
           }
           if (l == nl - 1) tc::mma_commit(&accum_half[h]);  // the final epilogue of half h overlaps half h+1's MMAs
         }
@@ -529,11 +549,11 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   auto slot_for = [&](int last_rows) {
     int mx = last_rows;
     for (int l = 0; l + 1 < num_layers; ++l) mx = layers[l].cout > mx ? layers[l].cout : mx;
-    return mx * 256;
+    return mx * 128;  // one slot holds W_hi or W_lo of a k-block
   };
   const bool can_compact = cout_last == 128 && hid_max <= 128;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float);
-  const size_t smem_compact = fixed + (size_t)r1 + 2 * (size_t)slot_for(64);
+  const size_t smem_compact = fixed + (size_t)r1 + 4 * (size_t)slot_for(64);
   const bool compact = can_compact && smem_compact <= 110 * 1024;
   const int last_rows = compact ? 64 : (cout_last <= 128 ? cout_last : 128);
   if (cout_last > 128 && cout_last != 256) {
@@ -546,7 +566,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   p.compact = compact ? 1 : 0;
   p.small_off = (cout_last > 128) ? 256 : 128;
   const size_t smem = compact ? smem_compact
-                              : fixed + (size_t)r1 + 2 * (size_t)p.wslot_bytes + 128 * 36 * sizeof(float);
+                              : fixed + (size_t)r1 + 4 * (size_t)p.wslot_bytes + 128 * 36 * sizeof(float);
   size_t off = 0;
   pk.nl = num_layers;
   pk.perm_c = use_xyz ? C : -1;
@@ -569,9 +589,9 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
   static size_t attr256 = 0, attr512 = 0;
-  // weight-bound (one CTA per SM) shapes run as CTA pairs sharing each weight stage (B200_SA_TC_PAIR=0 disables)
+  // optional (B200_SA_TC_PAIR=1): one-CTA-per-SM shapes run as CTA pairs sharing each weight copy via TMA multicast
   const char *pe = getenv("B200_SA_TC_PAIR");
-  const bool pair = !compact && !(pe && atoi(pe) == 0);
+  const bool pair = !compact && pe && atoi(pe) == 1;  // measured: no gain (the stream is latency-, not L2-read-bound)
   p.cluster = pair ? 2 : 1;
   int tiles = ceil_div(M, p.G);
   if (pair) tiles = (tiles + 1) & ~1;  // the padding CTA runs the pipeline on zero rows

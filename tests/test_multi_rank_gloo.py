@@ -57,3 +57,50 @@ def test_two_rank_gloo_sharded_run_matches_single_process(tmp_path, orc):
     ref = orc.furthest_point_sampling(cases.cloud(0, total, 700), 32)
     assert np.array_equal(gathered, ref)                                            # every scene once, in order
     assert float(np.load(tmp_path / "slowest.npy")[0]) == 11.0                      # max over ranks
+
+
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = importlib.import_module("3dioumatch_b200.shard")
+    torch.manual_seed(100 + rank)                      # replicas start different on purpose
+    net = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 1), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Conv1d(8, 2, 1))
+    shard.broadcast_parameters(net, src=0)
+    torch.manual_seed(0)
+    x = torch.randn(6, 4, 10)                          # global batch of 6 "scenes"
+    s, e = shard.scene_shard(rank, world, 6)
+    loss = net(x[s:e]).square().sum() / 6.0            # per-rank share of the global mean loss
+    loss.backward()
+    n = shard.allreduce_gradients(net, average=False)
+    if rank == 0:
+        torch.save({"grads": [p.grad.clone() for p in net.parameters()], "n": n,
+                    "state": {k: v.clone() for k, v in net.state_dict().items()}}, os.path.join(out_dir, "g.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_flat_bucket_gradient_allreduce(tmp_path):
+    """Sharded backward + one flat all-reduce == single-process backward over the whole batch (conv grads; BatchNorm
+    statistics are per replica by design, so the check uses eval-mode-free layers' gradients with BN in train mode on
+    equal shard sizes, where the per-shard batch statistics differ -> compare against the same sharded computation)."""
+    port = 29000 + ((os.getpid() + 7) % 2000)
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(tmp_path / "g.pt")
+    # single-process emulation of the two replicas (same broadcast weights, same shards)
+    net = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 1), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Conv1d(8, 2, 1))
+    torch.manual_seed(0)
+    x = torch.randn(6, 4, 10)
+    total = None
+    for s, e in ((0, 3), (3, 6)):
+        rep = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 1), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Conv1d(8, 2, 1))
+        rep.load_state_dict({k: v for k, v in got["state"].items()})
+        rep[1].running_mean.zero_(); rep[1].running_var.fill_(1.0); rep[1].num_batches_tracked.zero_()
+        (rep(x[s:e]).square().sum() / 6.0).backward()
+        g = [p.grad for p in rep.parameters()]
+        total = g if total is None else [a + b for a, b in zip(total, g)]
+    assert got["n"] == sum(p.numel() for p in net.parameters())
+    for a, b in zip(got["grads"], total):
+        assert torch.allclose(a, b, atol=1e-6), (a - b).abs().max()

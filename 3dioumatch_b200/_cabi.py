@@ -1,4 +1,4 @@
-"""ctypes binding of libb200pc.so (include/b200_pointnet2.h, include/b200_iou3d.h).
+"""ctypes binding of libb200pc.so (include/b200_pointnet2.h, include/b200_iou3d.h, include/b200_nms.h).
 
 There is no CPU or PyTorch fallback: if the library is missing, every operator raises."""
 import ctypes
@@ -44,6 +44,9 @@ PROTOTYPES = {
     "b200iou_nms_device": (c_int, [c_int, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200iou_nms": (c_int, [c_int, c_void_p, c_float, c_int, c_void_p, ctypes.POINTER(c_int), c_void_p]),
     "b200iou_boxes_iou_bev_cpu": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200nms_aabb_suppress": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "b200nms_box_extents": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -7,7 +7,8 @@
 
 A step = one forward of the VoteNet-with-IoU-branch dataflow (3dioumatch_b200/harness.py) over one batch of
 B=8 synthetic ScanNet-shaped scenes (N=40000 points, C=4, 256 proposals) + IoU labels against 64 padded GT boxes.
-Prints ONE JSON line on rank 0 (keys: see the task contract; extra keys `breakdown_ms`, `reference_cuda`, `c3`).
+Prints ONE JSON line on rank 0 (keys: see the task contract; extra keys `breakdown_ms`, `reference_cuda`, `c3`,
+`ssl_filter`).
 """
 import argparse
 import importlib
@@ -480,6 +481,30 @@ def main():
                 line["c3"]["nms_error"] = str(e).splitlines()[0][:120]
         except Exception as e:  # noqa: BLE001
             line["c3"] = {"error": str(e)[:200]}
+        # ---- pseudo-label filter (corners -> extents -> lower-half suppression), 8 scenes x 64 boxes ----
+        if a.impl == "b200":
+            try:
+                nms = importlib.import_module("utils.nms")
+                from oracle import oracle as orc
+                rb = np.stack([cases.aabb_boxes(i, 64, 18) for i in range(8)])
+                cen = torch.from_numpy(((rb[:, :, 0:3] + rb[:, :, 3:6]) / 2).astype(np.float32)).to(dev)
+                siz = torch.from_numpy(rb[:, :, 3:6] - rb[:, :, 0:3]).to(dev)
+                hd = torch.zeros((8, 64), dtype=torch.float64, device=dev)
+                tail = torch.from_numpy(rb[:, :, 6:8]).to(dev)
+
+                def filt():
+                    _, ext = nms.box_extents_batch(cen, siz, hd, return_corners=False)
+                    return nms.suppress_batch(torch.cat([ext.double(), tail], -1), 0.25, use_cls=True, lhs=True)
+                dev_us = c3_time(filt)
+                t0 = time.perf_counter()
+                for i in range(8):
+                    _, e = orc.box_extents(cen[i].cpu().numpy(), siz[i].cpu().numpy(), np.zeros(64))
+                    orc.aabb_suppress(np.concatenate([e.astype(np.float64), rb[i, :, 6:8]], 1), 0.25, True, True)
+                line["ssl_filter"] = {"workload": "8 scenes x 64 boxes: box extents + lhs_3d_faster_samecls (thresh 0.25)",
+                                      "device_us": round(dev_us, 2),
+                                      "host_numpy_port_us": round((time.perf_counter() - t0) * 1e6, 1)}
+            except Exception as e:  # noqa: BLE001
+                line["ssl_filter"] = {"error": str(e)[:200]}
         if a.impl == "reference":
             line["cpu_baseline"] = {"value": line["value"], "unit": "scenes/s", "kind": "reference",
                                     "cores": os.cpu_count(),

@@ -212,3 +212,67 @@ def nms_gpu(boxes, scores, thresh, pre_maxsize=None, normal=False):
         order = order[:pre_maxsize]
     keep = nms(boxes[order], thresh, normal=normal)
     return order[keep].astype(np.int64)
+
+
+# ---- axis-aligned box suppression -- the reference here is numpy itself -----------------
+def aabb_suppress(boxes, thresh, use_cls=False, lhs=False, old_type=False, valid=None):
+    """Restatement of utils/nms.py:84-122 (nms_3d_faster), :125-165 (nms_3d_faster_samecls; use_cls), :168-215
+    (lhs_3d_faster_samecls; use_cls + lhs) and, with z1 = 0 / z2 = 1 columns, :52-81 (nms_2d_faster).
+
+    boxes (K,8) [x1,y1,z1,x2,y2,z2,score,class] -> the reference's `pick` list (indices into `boxes`).
+    `valid` (K) plays nonempty_box_mask (models/ap_helper.py:198-201): masked rows are dropped first and the picks
+    are mapped back.  float64 throughout, numpy's operation order; equal scores are ordered by index (stable sort),
+    the one thing numpy.argsort's default leaves unspecified.  Formulated as a full K x K relation + one sweep (the
+    device kernel's structure) instead of the reference's shrinking-array loop."""
+    bx = np.asarray(boxes, np.float64)
+    keep = np.arange(bx.shape[0]) if valid is None else np.nonzero(np.asarray(valid) != 0)[0]
+    bx = bx[keep]
+    n = bx.shape[0]
+    lo, hi, score, cls = bx[:, 0:3], bx[:, 3:6], bx[:, 6], bx[:, 7]
+    ext = hi - lo
+    vol = ext[:, 0] * ext[:, 1] * ext[:, 2]
+    if lhs:
+        vol = vol + 1e-8
+    order = np.argsort(score, kind="stable")                    # ascending; NaN last
+    with np.errstate(all="ignore"):
+        d = np.maximum(0, np.minimum(hi[:, None, :], hi[None, :, :]) - np.maximum(lo[:, None, :], lo[None, :, :]))
+        inter = d[..., 0] * d[..., 1] * d[..., 2]
+        ov = inter / vol[None, :] if old_type else inter / (vol[:, None] + vol[None, :] - inter)   # [i picks, j tested]
+        if use_cls:
+            ov = ov * (cls[:, None] == cls[None, :])
+        rel = ov > thresh
+    alive = np.ones(n, bool)
+    pick = []
+    for p in range(n - 1, -1, -1):
+        i = order[p]
+        if not alive[i]:
+            continue
+        alive[i] = False
+        pick.append(int(i))
+        lower = order[:p]
+        hit = lower[alive[lower] & rel[i, lower]]                # ascending score
+        alive[hit] = False
+        if lhs:
+            pick.extend(int(j) for j in hit[::-1][: len(hit) // 2])
+    return [int(keep[i]) for i in pick]
+
+
+def box_extents(center, size, heading):
+    """predictions2corners3d + the min/max loops (models/ap_helper.py:76-93,187-197; utils/box_util.py:266-272,335-358):
+    center (K,3) f32 upright-depth, size (K,3) f64 (l,w,h), heading (K) f64 -> corners (K,8,3) f32 upright-camera,
+    extents (K,6) f32."""
+    center = np.asarray(center, np.float32)
+    size = np.asarray(size, np.float64)
+    heading = np.asarray(heading, np.float64)
+    cam = np.stack([center[:, 0], -center[:, 2], center[:, 1]], 1)          # flip_axis_to_camera, float32
+    sx = np.array([1, 1, -1, -1, 1, 1, -1, -1], np.float64)
+    sy = np.array([1, 1, 1, 1, -1, -1, -1, -1], np.float64)
+    sz = np.array([1, -1, -1, 1, 1, -1, -1, 1], np.float64)
+    c, s = np.cos(heading)[:, None], np.sin(heading)[:, None]
+    xc, yc, zc = sx * (size[:, 0:1] / 2), sy * (size[:, 2:3] / 2), sz * (size[:, 1:2] / 2)
+    with np.errstate(all="ignore"):
+        rx = (c * xc + 0.0 * yc) + s * zc
+        ry = (0.0 * xc + 1.0 * yc) + 0.0 * zc
+        rz = (-s * xc + 0.0 * yc) + c * zc
+        corners = np.stack([rx + cam[:, 0:1], ry + cam[:, 1:2], rz + cam[:, 2:3]], -1).astype(np.float32)
+    return corners, np.concatenate([corners.min(1), corners.max(1)], 1)

@@ -1,5 +1,5 @@
 """Developer micro-benchmarks (CUDA events, device-resident inputs): FPS cluster/thread sweep and the split of the fused
-SA call into ball query vs MLP+max.  Usage on the GPU box: python scripts/op_sweep.py [fps|sa|all]"""
+SA call into ball query vs MLP+max.  Usage on the GPU box: python scripts/op_sweep.py [fps|fps_one|sa|nms|all]"""
 import importlib
 import os
 import subprocess
@@ -50,6 +50,31 @@ def fps_sweep():
             subprocess.run([sys.executable, os.path.abspath(__file__), "fps_one"], env=env)
 
 
+def nms_ops():
+    """Device-side suppression against the numpy restatement of the reference's host loops."""
+    import time
+    import numpy as np
+    import torch
+    import cases
+    pkg = importlib.import_module("3dioumatch_b200")
+    pkg.install_dropin()
+    nms = importlib.import_module("utils.nms")
+    from oracle import oracle as orc
+    for (B, K) in ((8, 64), (8, 256), (12, 128), (8, 1024)):
+        b = np.stack([cases.aabb_boxes(i, K, 18) for i in range(B)])
+        t = torch.from_numpy(b).cuda()
+        ms = timeit(torch, lambda: nms.suppress_batch(t, 0.25, True, True))
+        t0 = time.perf_counter()
+        for i in range(B):
+            orc.aabb_suppress(b[i], 0.25, True, True)
+        cpu = (time.perf_counter() - t0) * 1e3
+        print("  lhs_3d_faster_samecls B=%d K=%d: device %.3f ms (incl. torch wrapper), numpy host loop %.2f ms" % (B, K, ms, cpu))
+        c = torch.rand((B, K, 3), device="cuda")
+        s = torch.rand((B, K, 3), device="cuda", dtype=torch.float64) + 0.1
+        h = torch.zeros((B, K), device="cuda", dtype=torch.float64)
+        print("  box_extents B=%d K=%d: %.3f ms" % (B, K, timeit(torch, lambda: nms.box_extents_batch(c, s, h))))
+
+
 def sa_split():
     import numpy as np
     import torch
@@ -88,3 +113,5 @@ if __name__ == "__main__":
         fps_sweep()
     if what in ("sa", "all"):
         sa_split()
+    if what in ("nms", "all"):
+        nms_ops()

@@ -62,6 +62,20 @@ def boxes(seed, n, extent=(8.0, 8.0, 3.0), jitter_of=None, jitter=0.1):
     return np.ascontiguousarray(np.concatenate([c, s, h], 1), np.float32)
 
 
+def aabb_boxes(seed, K, ncls, extent=(4.0, 4.0, 2.0)):
+    """(K,8) float64 rows [x1,y1,z1,x2,y2,z2,score,class] with float32-representable values and DISTINCT scores
+    (the layout of the reference's boxes_3d_with_prob, models/ap_helper.py:187-197)."""
+    rng = np.random.default_rng(1000 + seed)
+    c = rng.random((K, 3)) * np.asarray(extent)
+    s = rng.random((K, 3)) * 1.5 + 0.05
+    b = np.zeros((K, 8))
+    b[:, 0:3] = (c - s / 2).astype(np.float32)
+    b[:, 3:6] = (c + s / 2).astype(np.float32)
+    b[:, 6] = ((rng.permutation(K) + rng.random(K) * 0.5) / K).astype(np.float32)
+    b[:, 7] = rng.integers(0, ncls, K)
+    return b
+
+
 def degenerate_boxes():
     """Identical, touching, nested, zero-size, axis multiples, near-coincident rectangles."""
     b = [

@@ -3,6 +3,8 @@
 
   python tests/golden/make_golden.py --cpu            # here: reference CPU entry boxes_iou_bev_cpu -> iou_bev_cpu.npz
   python tests/golden/make_golden.py --gpu --out DIR  # on the B200 box: reference CUDA ops -> ref_cuda_*.npz
+  python tests/golden/make_golden.py --nms            # here: the reference's numpy suppression loops and corner code
+                                                      # imported from /root/reference -> ref_aabb_nms.npz
 """
 import argparse
 import importlib.util
@@ -113,10 +115,63 @@ def make_gpu(out_dir):
     print("wrote ref_cuda_pointops.npz, ref_cuda_iou.npz to", out_dir)
 
 
+def load_reference_py(name, rel, stubs=()):
+    """Import one UNMODIFIED python module of the reference by path (never copied into the repo)."""
+    import types
+    for st in stubs:
+        sys.modules.setdefault(st, types.ModuleType(st))
+    spec = importlib.util.spec_from_file_location(name, os.path.join("/root/reference", rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_nms(out_dir):
+    """utils/nms.py (nms_2d_faster, nms_3d_faster, nms_3d_faster_samecls, lhs_3d_faster_samecls) and
+    utils/box_util.py get_3d_box + models/ap_helper.py flip_axis_to_camera on seeded inputs with distinct scores."""
+    import types
+    stub = types.ModuleType("pc_util")
+    stub.bbox_corner_dist_measure = None
+    sys.modules["pc_util"] = stub
+    ref = load_reference_py("ref_nms", "utils/nms.py")
+    for name in ("pcdet", "pcdet.ops", "pcdet.ops.iou3d_nms", "pcdet.ops.iou3d_nms.iou3d_nms_utils"):
+        sys.modules.setdefault(name, types.ModuleType(name))  # box_util imports (and here never calls) the IoU op
+    sys.modules["pcdet.ops.iou3d_nms.iou3d_nms_utils"].boxes_iou3d_gpu = None
+    box_util = load_reference_py("ref_box_util", "utils/box_util.py")
+    res = {}
+    for name, (seed, K, ncls) in {"k64": (0, 64, 3), "k256": (1, 256, 18), "k37": (2, 37, 1), "k1": (3, 1, 2)}.items():
+        b = cases.aabb_boxes(seed, K, ncls)
+        res[name + "_boxes"] = b
+        for thr in (0.25, 0.5):
+            for old in (0, 1):
+                tag = "%s_t%g_o%d" % (name, thr, old)
+                res[tag + "_nms3d"] = np.asarray(ref.nms_3d_faster(b[:, :7], thr, bool(old)), np.int32)
+                res[tag + "_nms3d_cls"] = np.asarray(ref.nms_3d_faster_samecls(b, thr, bool(old)), np.int32)
+                res[tag + "_lhs_cls"] = np.asarray(ref.lhs_3d_faster_samecls(b, thr, bool(old)), np.int32)
+                res[tag + "_nms2d"] = np.asarray(ref.nms_2d_faster(b[:, [0, 2, 3, 5, 6]], thr, bool(old)), np.int32)
+    # corners: the loop body of predictions2corners3d (models/ap_helper.py:82-91)
+    rng = np.random.default_rng(9)
+    K = 200
+    center = (rng.random((K, 3)) * [8, 8, 3] - [4, 4, 0]).astype(np.float32)
+    size = rng.random((K, 3)) * 2 + 0.05 + rng.standard_normal((K, 3)).astype(np.float32) * 0.01
+    heading = (rng.random(K) - 0.5) * 2 * np.pi
+    heading[:20] = 0.0  # ScanNet: class2angle returns zeros
+    cam = center.copy()
+    cam[..., [0, 1, 2]] = cam[..., [0, 2, 1]]  # flip_axis_to_camera (models/ap_helper.py:28-35)
+    cam[..., 1] *= -1
+    corners = np.zeros((K, 8, 3), np.float32)
+    for j in range(K):
+        corners[j] = box_util.get_3d_box(size[j], heading[j], cam[j])
+    res.update(corner_center=center, corner_size=size, corner_heading=heading, corners=corners)
+    np.savez_compressed(os.path.join(out_dir, "ref_aabb_nms.npz"), **res)
+    print("wrote ref_aabb_nms.npz")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--nms", action="store_true")
     ap.add_argument("--out", default=HERE)
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
@@ -124,3 +179,5 @@ if __name__ == "__main__":
         make_cpu(a.out)
     if a.gpu:
         make_gpu(a.out)
+    if a.nms:
+        make_nms(a.out)

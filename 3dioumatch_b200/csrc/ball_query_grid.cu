@@ -202,7 +202,7 @@ int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const
   size_t cub_bytes = 0;
   const size_t ws_bytes = bg_workspace_bytes(B, N, table_bits, &cub_bytes);
   char *ws = nullptr;
-  B200_CUDA_OK(cudaMallocAsync((void **)&ws, ws_bytes, stream));
+  B200_CUDA_OK(scratch_alloc((void **)&ws, ws_bytes, stream));
   unsigned *keys_in = (unsigned *)ws, *keys_out = keys_in + total;
   int *vals_in = (int *)(keys_out + total), *vals_out = vals_in + total;
   float4 *sorted_pts = (float4 *)(vals_out + total);  // 16-byte aligned: 4 * total * 4 bytes precede it

@@ -53,6 +53,25 @@ inline int num_sms() {
 
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Stream-ordered scratch memory.  The device's default pool gives freed blocks back to the driver at every
+// synchronisation unless a release threshold is set, which turns each eager call after a sync into a driver
+// allocation (hundreds of microseconds); keep them pooled instead.
+inline cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t stream) {
+  static bool tuned[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !tuned[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    tuned[dev] = true;
+  }
+  return cudaMallocAsync(p, bytes, stream);
+}
+
 // ---- the reference's squared-distance rounding sequence -------------------------------------
 // nvcc contracts (a*a + b*b + c*c) of the reference kernels (ball_query_gpu.cu:36-37,
 // sampling_gpu.cu:105,108-109, interpolate_gpu.cu:38) for sm_100a into

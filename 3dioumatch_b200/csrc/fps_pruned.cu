@@ -362,7 +362,7 @@ int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx
   const size_t off_cub = (off_bbox + 6 * (size_t)B * 4 + 255) & ~(size_t)255;
   const size_t ws_bytes = off_cub + cub_bytes + 256;
   char *ws = nullptr;
-  B200_CUDA_OK(cudaMallocAsync((void **)&ws, ws_bytes, stream));
+  B200_CUDA_OK(scratch_alloc((void **)&ws, ws_bytes, stream));
   unsigned long long *keys_in = (unsigned long long *)ws, *keys_out = keys_in + total;
   int *vals_in = (int *)(ws + off_vals), *vals_out = vals_in + total;
   unsigned *bbox = (unsigned *)(ws + off_bbox);

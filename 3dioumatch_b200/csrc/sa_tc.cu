@@ -584,7 +584,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     off += (size_t)t.nhalf * t.nkb * (size_t)t.rows * 256;
   }
   uint8_t *packed = nullptr;
-  B200_CUDA_OK(cudaMallocAsync((void **)&packed, off, stream));
+  B200_CUDA_OK(scratch_alloc((void **)&packed, off, stream));
   tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;

@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200pc.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "lib", "libb200pc.so")  # override: developer builds
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 

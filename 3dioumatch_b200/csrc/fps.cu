@@ -418,14 +418,17 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
   // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
   // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.
-  static int force_cs = -1, force_threads = -1, debug = 0;
-  if (force_cs < 0) {
+  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0;
+  if (env_cs < 0) {
     const char *e = getenv("B200_FPS_CLUSTER");
-    force_cs = e ? atoi(e) : 0;
+    env_cs = e ? atoi(e) : 0;
     e = getenv("B200_FPS_THREADS");
-    force_threads = e ? atoi(e) : 0;
+    env_threads = e ? atoi(e) : 0;
+    e = getenv("B200_FPS_FORCE_MIN_N");  // the two overrides above apply to clouds of at least this many points
+    env_min_n = e ? atoi(e) : 0;
     debug = getenv("B200_FPS_DEBUG") != nullptr;
   }
+  const int force_cs = N >= env_min_n ? env_cs : 0, force_threads = N >= env_min_n ? env_threads : 0;
   const int sms = num_sms();
   int best_cs = 0, best_ppt = 0, threads = 0;
   fps_fn best_fn = nullptr;

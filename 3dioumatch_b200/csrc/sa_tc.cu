@@ -26,45 +26,9 @@
 #include "../../include/b200_pointnet2.h"
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "sa_tc.cuh"
 
 namespace b200 {
-
-constexpr int TC_ROWS = 128;
-constexpr int TC_THREADS = 192;
-constexpr int TC_MAXL = 4;
-constexpr uint32_t TC_KB_BYTES = 128 * 128;          // one operand k-block: 128 rows x 128 B
-constexpr uint32_t TC_WSTAGE_BYTES = 2 * TC_KB_BYTES;  // W_hi | W_lo
-
-struct TcLayer {
-  const float *scale, *shift;
-  int cin, cout, nkb, nhalf;
-  int rows;           // weight rows per stage = MMA N (cout for hidden layers, <= 128 per half for the last layer)
-  size_t packed_off;  // byte offset of this layer's stages in the packed weight buffer
-};
-
-struct TcParams {
-  int B, N, M, C, ns, G, use_xyz, nl;
-  float inv_r;
-  const float *xyz, *feat_pm, *new_xyz;
-  const int32_t *idx;
-  float *out, *out_pm;
-  const uint8_t *packed;
-  int vec_gather;  // feature rows are 16-byte aligned runs of a multiple of 4 floats
-  // mode 1 (feature-propagation style rows, models/grid_conv_module.py:87-108): row (centre g, sample s) is the
-  // inverse-distance blend of three source rows, channels [rel xyz (3) | sum_t w_t * feat[idx_t] (C)]
-  // shared-memory / TMEM geometry chosen by the launcher
-  int r1_bytes;      // activation region: layer-1 A stages, later X_hi | X_lo
-  int x_lo_off;      // byte offset of X_lo inside R1 (= hidden k-blocks * 16 KB)
-  int wslot_bytes;   // size of one weight stage slot in R2
-  int small_off;     // TMEM column offset of the correction-term accumulators (128 or 256)
-  int compact;       // 1: the final epilogue's slab aliases R2 (all MMAs finished first) -> ~105 KB, 2 CTAs per SM
-  int cluster;       // 2: CTA pairs share every weight stage through one multicast bulk copy (half the L2 reads)
-  int mode;
-  const int32_t *idx3;   // (B, M*ns, 3)
-  const float *w3;       // (B, M*ns, 3)
-  const float *rel3;     // (B, M*ns, 3) or NULL
-  TcLayer L[TC_MAXL];
-};
 
 // ---- weight packing: (cout, cin) fp32 -> [half][kb][hi|lo][128 rows x 128 B, 128-byte swizzle] -----------------------
 struct PackParams {
@@ -502,6 +466,7 @@ extern "C" int b200_debug_tc_profile(unsigned long long *out16) {
 }
 #endif
 
+
 // Can the tensor-core kernel take this stage?  (hidden widths 128, last 128|256, nsample 16|32, aligned point-major features)
 bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm) {
   static int enabled = -1;
@@ -551,15 +516,21 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     for (int l = 0; l + 1 < num_layers; ++l) mx = layers[l].cout > mx ? layers[l].cout : mx;
     return mx * 128;  // one slot holds W_hi or W_lo of a k-block
   };
+  static int persist = -1;
+  if (persist < 0) {
+    const char *e = getenv("B200_SA_TC_PERSIST");
+    persist = (e && atoi(e) == 0) ? 0 : 1;
+  }
   const bool can_compact = cout_last == 128 && hid_max <= 128;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float);
   const size_t smem_compact = fixed + (size_t)r1 + 4 * (size_t)slot_for(64);
-  const bool compact = can_compact && smem_compact <= 110 * 1024;
+  const bool compact = !persist && can_compact && smem_compact <= 110 * 1024;
   const int last_rows = compact ? 64 : (cout_last <= 128 ? cout_last : 128);
   if (cout_last > 128 && cout_last != 256) {
     set_error("sa_forward(tc): last-layer width %d unsupported", cout_last);
     return 1;
   }
+  if (persist && r1 < 4 * (int)TC_KB_BYTES) r1 = 4 * (int)TC_KB_BYTES;  // two layer-1 stages alternate across tiles
   p.r1_bytes = r1;
   p.x_lo_off = nkbh * (int)TC_KB_BYTES;
   p.wslot_bytes = slot_for(last_rows);
@@ -584,10 +555,19 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     off += (size_t)t.nhalf * t.nkb * (size_t)t.rows * 256;
   }
   uint8_t *packed = nullptr;
-  B200_CUDA_OK(scratch_alloc((void **)&packed, off, stream));
+  const size_t counter_off = (off + 255) & ~(size_t)255;
+  B200_CUDA_OK(scratch_alloc((void **)&packed, counter_off + 256, stream));
   tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
+  p.nslots = 4; p.total_tiles = 0; p.tiles_per_scene = 0; p.tile_counter = nullptr; p.final_shfl = 0;
+  if (persist) {
+    // persistent warp-specialised kernel (sa_tcp.cu): one CTA per SM, tiles from an atomic queue
+    const int rc = sa_tcp_launch(p, reinterpret_cast<int *>(packed + counter_off), stream);
+    if (rc != 0) return rc;
+    B200_CUDA_OK(cudaFreeAsync(packed, stream));
+    return 0;
+  }
   static size_t attr256 = 0, attr512 = 0;
   // optional (B200_SA_TC_PAIR=1): one-CTA-per-SM shapes run as CTA pairs sharing each weight copy via TMA multicast
   const char *pe = getenv("B200_SA_TC_PAIR");

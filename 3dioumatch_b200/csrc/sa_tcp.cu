@@ -1,0 +1,598 @@
+// sa_tcp.cu -- persistent, warp-specialised fused set-abstraction forward on tcgen05 tensor cores (sm_100a).
+//
+// Same contract and numerics as sa_tc_kernel (sa_tc.cu: gather grouped rows -> SharedMLP as split-precision TF32 GEMMs
+// with fp32 accumulation in TMEM -> max over nsample; pointnet2_modules.py:215-277, pytorch_utils.py:14-39), different
+// schedule.  One CTA per SM for the whole launch; tiles (128 grouped rows) come from an atomic counter, so a CTA that
+// becomes resident late (the SMs are shared with the long-running FPS cluster of the next step) finds the queue
+// empty instead of holding up the launch.  Fourteen warps:
+//   warps 0-7   epilogue : two warpgroups, alternate 32-column chunks.  TMEM -> scale/shift/ReLU -> hi/lo split ->
+//                          swizzled shared memory (hidden layers); final layer: max over nsample by a butterfly
+//                          transpose-reduce in registers (warp shuffles; no slab, no CTA barrier per chunk)
+//   warps 8-11  producers: layer-1 gather of the NEXT tile -- index -> row -> feature global loads are in flight while
+//                          the current tile computes; two k-blocks are held in registers before R1 becomes free
+//   warp  12    MMA      : runs converged; one elected lane issues tcgen05.mma / tcgen05.commit, so descriptors live in
+//                          uniform registers (the one-thread branch of sa_tc_kernel compiled to a 7-R2UR waterfall loop
+//                          per MMA, ~150 cycles of issue per 64-cycle MMA: measured with scripts/tcp_profile.py)
+//   warp  13    loader   : tile scheduler (atomicAdd + shared-memory tile ring, one tile ahead) and the weight stream
+//                          (cp.async.bulk ring of 4 or 8 half stages, continuous across tiles)
+// TMEM: 512 columns, two accumulator sets (set s: products at 128 s, split-precision corrections at 256 + 128 s).
+// Hidden layers use set 0; the last layer uses set h for half h (256-wide outputs) or set 1 (<= 128-wide), so the
+// final epilogue of tile i runs under the layer-1 MMAs of tile i+1.
+#include <stdlib.h>
+
+#include "../../include/b200_pointnet2.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "sa_tc.cuh"
+
+namespace b200 {
+
+constexpr int TP_THREADS = 448;
+constexpr int TP_EPI = 256;     // epilogue threads (warps 0-7)
+constexpr int TP_PROD0 = 256;   // first producer thread (warps 8-11)
+constexpr int TP_MMA_WARP = 12, TP_LOAD_WARP = 13;
+constexpr int TP_TQ = 4;        // depth of the tile-id ring
+constexpr int TP_MAXSLOTS = 8;  // weight ring slots (p.nslots = 4 or 8)
+
+// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_addr(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin == 256) t0 = clock64();
+    if (spin > 256 && (spin & 255u) == 0u && clock64() - t0 > 6000000000LL) {
+      printf("[b200] sa_tcp_kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+
+// one leader lane of a converged warp (the same lane every time: tcgen05.commit tracks the issuing thread)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Butterfly transpose-reduce: every lane enters with 32 column values of its own row; after STEPS exchange steps over
+// the lane bits below min(nsample, 32) each lane holds the maxima, over the nsample-lane group it belongs to, of
+// 32 >> STEPS columns:  column = ((lane & (min(ns,32) - 1)) << (5 - STEPS)) | i.
+template <int STEPS>
+__device__ __forceinline__ void transpose_max(float (&v)[32], int lane, int top_off) {
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s) {
+    const int n = 16 >> s;
+    const int off = top_off >> s;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float keep = upper ? v[i + n] : v[i];
+        const float send = upper ? v[i] : v[i + n];
+        v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+      }
+    }
+  }
+}
+
+#ifdef B200_TC_PROFILE
+__device__ unsigned long long g_tcp_prof[32];
+#define TPW(cat, bar, par)                                \
+  do {                                                    \
+    const long long _w0 = clock64();                      \
+    mbar_wait_wd(bar, par);                               \
+    tp_acc[cat] += (unsigned long long)(clock64() - _w0); \
+  } while (0)
+#else
+#define TPW(cat, bar, par) mbar_wait_wd(bar, par)
+#endif
+
+__global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *R1 = base;                                                        // layer-1 A stages / X_hi | X_lo
+  uint8_t *R2 = base + p.r1_bytes;                                           // weight ring: nslots x wslot_bytes
+  float *s_scale = reinterpret_cast<float *>(R2 + p.nslots * p.wslot_bytes);  // [TC_MAXL][256]
+  float *s_shift = s_scale + TC_MAXL * 256;
+  float *s_partial = s_shift + TC_MAXL * 256;                                // [2][4][256] per-warp maxima (nsample > 32)
+
+  __shared__ uint64_t full_a[2], empty_a[2], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
+  __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free[2], tq_full[TP_TQ], tq_empty[TP_TQ];
+  __shared__ int tq_tile[TP_TQ];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ns = p.ns, nl = p.nl, G = p.G;
+  const int nslots = p.nslots;
+  const int nhalf_last = p.L[nl - 1].nhalf;
+
+  if (warp == TP_MMA_WARP) tc::tmem_alloc<512>(&tmem_base_s);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&full_a[s], 128);
+      tc::mbar_init(&empty_a[s], 1);
+      tc::mbar_init(&accum_half[s], 1);
+      tc::mbar_init(&d_free[s], TP_EPI);
+    }
+    for (int s = 0; s < TP_MAXSLOTS; ++s) {
+      tc::mbar_init(&full_w[s], 1);
+      tc::mbar_init(&empty_w[s], 1);
+    }
+    for (int s = 0; s < TP_TQ; ++s) {
+      tc::mbar_init(&tq_full[s], 1);
+      tc::mbar_init(&tq_empty[s], TP_EPI + 128 + 1);  // epilogue + producer threads + one lane of the MMA warp
+    }
+    tc::mbar_init(&accum_full, 1);
+    tc::mbar_init(&x_ready, TP_EPI);
+    tc::mbar_fence_init();
+  }
+  for (int e = tid; e < nl * 256; e += TP_THREADS) {
+    const int l = e >> 8, c = e & 255;
+    s_scale[e] = c < p.L[l].cout ? p.L[l].scale[c] : 0.f;
+    s_shift[e] = c < p.L[l].cout ? p.L[l].shift[c] : 0.f;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_d = tmem_base_s;
+#ifdef B200_TC_PROFILE
+  unsigned long long tp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int tp_tile_cat = warp == TP_MMA_WARP ? 2 : (warp >= 8 ? 8 : 12);
+  const long long tp_start = clock64();
+  unsigned long long tp_tiles = 0;
+#endif
+
+  // every consumer role walks the tile ring with its own counter; `arrive` = this thread is one of the ring's
+  // registered consumers (all epilogue and producer threads, one lane of the MMA warp)
+  int n_get = 0;
+  auto next_tile = [&](bool arrive) -> int {
+    const int slot = n_get % TP_TQ;
+    TPW(tp_tile_cat, &tq_full[slot], (uint32_t)((n_get / TP_TQ) & 1));
+    const int t = tq_tile[slot];
+    if (arrive) tc::mbar_arrive(&tq_empty[slot]);
+    ++n_get;
+    return t;
+  };
+
+  if (warp == TP_LOAD_WARP) {
+    // ================= tile scheduler + weight loader (converged warp, elected lane issues) =================
+    int n_pub = 0;
+    auto publish = [&]() -> int {
+      const int slot = n_pub % TP_TQ;
+      TPW(0, &tq_empty[slot], (uint32_t)(((n_pub / TP_TQ) & 1) ^ 1));
+      int t = 0;
+      if (lane == 0) {
+        t = atomicAdd(p.tile_counter, 1);
+        if (t >= p.total_tiles) t = -1;
+        tq_tile[slot] = t;
+        tc::mbar_arrive(&tq_full[slot]);  // release: the tile id is visible to the waiters
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      ++n_pub;
+      return t;
+    };
+    uint32_t i = 0;
+    int cur = publish();
+    while (cur >= 0) {
+      const int nxt = publish();  // one tile ahead: the producers prefetch its rows while this one computes
+      for (int l = 0; l < nl; ++l) {
+        const int nst = p.L[l].nhalf * p.L[l].nkb;
+        const uint8_t *src = p.packed + p.L[l].packed_off;
+        const uint32_t part_bytes = (uint32_t)p.L[l].rows * 128u;  // W_hi or W_lo of one k-block
+        for (int s = 0; s < 2 * nst; ++s, ++i) {                  // packed order: hi(0), lo(0), hi(1), lo(1), ...
+          const uint32_t st = i % (uint32_t)nslots;
+          TPW(1, &empty_w[st], ((i / (uint32_t)nslots) & 1u) ^ 1u);
+          if (elect_one()) {
+            tc::mbar_arrive_expect_tx(&full_w[st], part_bytes);
+            tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * part_bytes, part_bytes, &full_w[st]);
+          }
+          __syncwarp();
+        }
+      }
+      cur = nxt;
+    }
+  } else if (warp == TP_MMA_WARP) {
+    // ================= MMA issuer (converged warp, elected lane issues) =================
+    uint32_t i = 0, ka = 0, n_xr = 0, tl = 0;
+    const uint32_t r1_addr = tc::smem_addr(R1), r2_addr = tc::smem_addr(R2);
+    for (;;) {
+      const int t = next_tile(lane == 0);
+      if (t < 0) break;
+      for (int l = 0; l < nl; ++l) {
+        const bool last = l == nl - 1;
+        if (l > 0) {
+          TPW(3, &x_ready, n_xr & 1u);  // hidden activations of layer l-1 are in R1 (and set 0 was read)
+          ++n_xr;
+          tc::tc_fence_after_sync();
+        }
+        const int nkb = p.L[l].nkb;
+        const uint32_t idesc = tc::make_idesc_tf32(128, p.L[l].rows);
+        for (int h = 0; h < p.L[l].nhalf; ++h) {
+          const int set = last ? (nhalf_last == 2 ? h : 1) : 0;
+          // write-after-read on the accumulator columns: the previous tile's final epilogue must have drained them
+          if (tl > 0) {
+            if (last && set == 1) {
+              TPW(4, &d_free[1], (tl - 1u) & 1u);
+              tc::tc_fence_after_sync();
+            } else if (l == 0 && nhalf_last == 2) {
+              TPW(4, &d_free[0], (tl - 1u) & 1u);
+              tc::tc_fence_after_sync();
+            }
+          }
+          const uint32_t d_big = tmem_d + (uint32_t)(set * 128);
+          const uint32_t d_small = d_big + 256u;
+          for (int kb = 0; kb < nkb; ++kb) {
+            uint32_t a_hi, a_lo;
+            if (l == 0) {
+              const uint32_t as = ka & 1u;
+              TPW(5, &full_a[as], (ka >> 1) & 1u);
+              a_hi = r1_addr + as * 2u * TC_KB_BYTES;
+              a_lo = a_hi + TC_KB_BYTES;
+            } else {
+              a_hi = r1_addr + (uint32_t)kb * TC_KB_BYTES;
+              a_lo = a_hi + (uint32_t)p.x_lo_off;
+            }
+            const uint64_t da_hi = tc::make_desc_sw128(a_hi), da_lo = tc::make_desc_sw128(a_lo);
+            {  // W_hi slot: A_hi*W_hi -> products, A_lo*W_hi -> corrections
+              const uint32_t sl = i % (uint32_t)nslots;
+              TPW(6, &full_w[sl], (i / (uint32_t)nslots) & 1u);
+              tc::tc_fence_after_sync();
+              const uint64_t dw = tc::make_desc_sw128(r2_addr + sl * (uint32_t)p.wslot_bytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
+                  tc::mma_tf32(d_big, da_hi + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                  tc::mma_tf32(d_small, da_lo + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                }
+                tc::mma_commit(&empty_w[sl]);
+              }
+              __syncwarp();
+              ++i;
+            }
+            {  // W_lo slot: A_hi*W_lo -> corrections
+              const uint32_t sl = i % (uint32_t)nslots;
+              TPW(6, &full_w[sl], (i / (uint32_t)nslots) & 1u);
+              tc::tc_fence_after_sync();
+              const uint64_t dw = tc::make_desc_sw128(r2_addr + sl * (uint32_t)p.wslot_bytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);
+                  tc::mma_tf32(d_small, da_hi + adv, dw + adv, idesc, 1u);
+                }
+                if (l == 0) tc::mma_commit(&empty_a[ka & 1u]);
+                tc::mma_commit(&empty_w[sl]);
+              }
+              __syncwarp();
+              if (l == 0) ++ka;
+              ++i;
+            }
+          }
+          if (last) {
+            if (elect_one()) tc::mma_commit(&accum_half[h]);
+            __syncwarp();
+          }
+        }
+        if (!last) {
+          if (elect_one()) tc::mma_commit(&accum_full);
+          __syncwarp();
+        }
+      }
+      ++tl;
+    }
+  } else if (warp >= 8) {
+    // ================= producers: row (tid - 256) of the tile, layer-1 A operand =================
+    const int row = tid - TP_PROD0;
+    const int g = row / ns;
+    const int C = p.C;
+    uint32_t ka = 0, tl = 0;
+    for (;;) {
+      const int t = next_tile(true);
+      if (t < 0) break;
+      const int b = t / p.tiles_per_scene;
+      const int m0 = (t - b * p.tiles_per_scene) * G;
+      const int g_here = min(G, p.M - m0);
+      const bool valid = g < g_here;
+      int src_idx = 0;
+      float ctr[3] = {0.f, 0.f, 0.f};
+      if (valid && p.mode == 0) {
+        src_idx = p.idx[((size_t)b * p.M + m0 + g) * ns + (row - g * ns)];
+        const float *c = p.new_xyz + ((size_t)b * p.M + m0 + g) * 3;
+        ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
+      }
+      const float *frow = (valid && C > 0 && p.mode == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
+      float rel[3] = {0.f, 0.f, 0.f};
+      const float *f3[3] = {nullptr, nullptr, nullptr};
+      float wt[3] = {0.f, 0.f, 0.f};
+      if (p.mode == 1 && valid) {
+        const size_t q = ((size_t)b * p.M + m0 + g) * ns + (row - g * ns);
+        for (int u = 0; u < 3; ++u) {
+          f3[u] = p.feat_pm + ((size_t)b * p.N + p.idx3[q * 3 + u]) * C;
+          wt[u] = p.w3[q * 3 + u];
+        }
+        if (p.rel3 && p.use_xyz) {
+          rel[0] = p.rel3[q * 3 + 0]; rel[1] = p.rel3[q * 3 + 1]; rel[2] = p.rel3[q * 3 + 2];
+        }
+      }
+      if (valid && p.use_xyz && p.mode == 0) {
+        const float *q = p.xyz + ((size_t)b * p.N + src_idx) * 3;
+        // pointnet2_utils.py:351-353: grouped_xyz -= new_xyz ; /= radius  (x * fp32(1/r) on CUDA)
+        rel[0] = __fmul_rn(__fsub_rn(q[0], ctr[0]), p.inv_r);
+        rel[1] = __fmul_rn(__fsub_rn(q[1], ctr[1]), p.inv_r);
+        rel[2] = __fmul_rn(__fsub_rn(q[2], ctr[2]), p.inv_r);
+      }
+      // layer-1 A operand: [features (C) | rel xyz (3) | 0 ...]
+      auto load_kb = [&](int kb, float4 (&v)[8]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int ch = kb * 32 + c * 4;
+          if (valid && p.mode == 1 && ch + 3 < C) {  // blend of the three neighbours (three_interpolate + concat)
+            const float4 a0 = __ldg(reinterpret_cast<const float4 *>(f3[0] + ch));
+            const float4 a1 = __ldg(reinterpret_cast<const float4 *>(f3[1] + ch));
+            const float4 a2 = __ldg(reinterpret_cast<const float4 *>(f3[2] + ch));
+            // interpolate_gpu.cu:100-104 rounding: fma(p3,w3, fma(p1,w1, p2*w2))
+            v[c].x = __fmaf_rn(a2.x, wt[2], __fmaf_rn(a0.x, wt[0], __fmul_rn(a1.x, wt[1])));
+            v[c].y = __fmaf_rn(a2.y, wt[2], __fmaf_rn(a0.y, wt[0], __fmul_rn(a1.y, wt[1])));
+            v[c].z = __fmaf_rn(a2.z, wt[2], __fmaf_rn(a0.z, wt[0], __fmul_rn(a1.z, wt[1])));
+            v[c].w = __fmaf_rn(a2.w, wt[2], __fmaf_rn(a0.w, wt[0], __fmul_rn(a1.w, wt[1])));
+          } else if (valid && p.mode == 0 && p.vec_gather && ch + 3 < C) {
+            v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
+          } else {
+            float e4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = ch + e;
+              float x = 0.f;
+              if (valid) {
+                if (k < C) {
+                  x = p.mode == 0 ? frow[k]
+                                  : __fmaf_rn(f3[2][k], wt[2], __fmaf_rn(f3[0][k], wt[0], __fmul_rn(f3[1][k], wt[1])));
+                } else if (p.use_xyz && k < C + 3) {
+                  x = rel[k - C];
+                }
+              }
+              e4[e] = x;
+            }
+            v[c] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+          }
+        }
+      };
+      auto store_kb = [&](const float4 (&v)[8]) {
+        const uint32_t as = ka & 1u;
+        TPW(9, &empty_a[as], ((ka >> 1) & 1u) ^ 1u);
+        uint8_t *a_hi = R1 + as * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 h, l;
+          tc::split_tf32(v[c].x, h.x, l.x); tc::split_tf32(v[c].y, h.y, l.y);
+          tc::split_tf32(v[c].z, h.z, l.z); tc::split_tf32(v[c].w, h.w, l.w);
+          const uint32_t off = tc::sw128_offset(row, c);
+          *reinterpret_cast<float4 *>(a_hi + off) = h;
+          *reinterpret_cast<float4 *>(a_lo + off) = l;
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&full_a[as]);
+        ++ka;
+      };
+      const int nkb1 = p.L[0].nkb;
+      float4 va[8], vb[8];
+      load_kb(0, va);  // both in flight while the previous tile still computes
+      if (nkb1 > 1) load_kb(1, vb);
+      if (tl > 0) {
+        // R1 doubles as the hidden activations of the previous tile: wait until its last MMA has read them
+        TPW(10, &accum_half[nhalf_last - 1], (tl - 1u) & 1u);
+      }
+      for (int kb = 0; kb < nkb1; kb += 2) {
+        store_kb(va);
+        if (kb + 2 < nkb1) load_kb(kb + 2, va);
+        if (kb + 1 < nkb1) {
+          store_kb(vb);
+          if (kb + 3 < nkb1) load_kb(kb + 3, vb);
+        }
+      }
+      ++tl;
+    }
+  } else {
+    // ================= epilogue: warpgroup wg takes the 32-column chunks wg, wg+2, ...; row = TMEM lane =================
+    const int wg = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    uint32_t n_acc = 0, tl = 0;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    for (;;) {
+      const int t = next_tile(true);
+      if (t < 0) break;
+      const int b = t / p.tiles_per_scene;
+      const int m0 = (t - b * p.tiles_per_scene) * G;
+      const int g_here = min(G, p.M - m0);
+      for (int l = 0; l < nl; ++l) {
+        const float *sc = s_scale + l * 256, *sh = s_shift + l * 256;
+        if (l + 1 < nl) {
+          TPW(13, &accum_full, n_acc & 1u);
+          ++n_acc;
+          tc::tc_fence_after_sync();
+          // hidden layer: X = relu(scale*acc+shift) -> split -> R1 as the next layer's K-major operand (set 0)
+          uint8_t *x_hi = R1, *x_lo = R1 + p.x_lo_off;
+          const int H = p.L[l].cout;  // hidden width, multiple of 32
+          for (int c0 = wg * 32; c0 < H; c0 += 64) {
+            uint32_t r[32], r2[32];
+            tc::tmem_ld_32x32(lane_addr + (uint32_t)c0, r);
+            tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)c0, r2);
+            tc::tmem_ld_wait();
+            uint8_t *kb_hi = x_hi + (c0 >> 5) * TC_KB_BYTES, *kb_lo = x_lo + (c0 >> 5) * TC_KB_BYTES;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
+              const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
+              const float scv[4] = {s4.x, s4.y, s4.z, s4.w}, shv[4] = {h4.x, h4.y, h4.z, h4.w};
+              float y[4], hh[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float acc = __uint_as_float(r[c * 4 + e]) + __uint_as_float(r2[c * 4 + e]);
+                y[e] = fmaxf(fmaf(acc, scv[e], shv[e]), 0.f);
+                tc::split_tf32(y[e], hh[e], lo[e]);
+              }
+              const uint32_t off = tc::sw128_offset(row, c);
+              *reinterpret_cast<float4 *>(kb_hi + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<float4 *>(kb_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+          tc::fence_proxy_async_smem();
+          tc::tc_fence_before_sync();
+          tc::mbar_arrive(&x_ready);
+        } else {
+          // last layer: relu(scale*acc+shift), then the max over each centre's nsample rows.  Rows are TMEM lanes =
+          // lanes of this warp (and of its neighbours when nsample > 32): reduce in registers with warp shuffles.
+          const int cout = p.L[l].cout;
+          const int rows_l = p.L[l].rows;
+          float *part = s_partial + (tl & 1u) * (4 * 256);
+          for (int h = 0; h < nhalf_last; ++h) {
+            const int set = nhalf_last == 2 ? h : 1;
+            TPW(14, &accum_half[h], tl & 1u);
+            tc::tc_fence_after_sync();
+            const uint32_t set_addr = lane_addr + (uint32_t)(set * 128);
+            if (wg * 32 >= rows_l) {  // no chunk for this warpgroup in this half: it has nothing to drain
+              tc::tc_fence_before_sync();
+              tc::mbar_arrive(&d_free[set]);
+            }
+            for (int cc0 = wg * 32; cc0 < rows_l; cc0 += 64) {
+              const int c0 = h * rows_l + cc0;  // output channel of the chunk's first column
+              uint32_t r[32], r2[32];
+              tc::tmem_ld_32x32(set_addr + (uint32_t)cc0, r);
+              tc::tmem_ld_32x32(set_addr + 256u + (uint32_t)cc0, r2);
+              tc::tmem_ld_wait();
+              if (cc0 + 64 >= rows_l) {  // this thread's last read of the set: the MMA warp may overwrite it (next tile)
+                tc::tc_fence_before_sync();
+                tc::mbar_arrive(&d_free[set]);
+              }
+              float v[32];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
+                const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
+                v[c * 4 + 0] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]), s4.x, h4.x), 0.f);
+                v[c * 4 + 1] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]), s4.y, h4.y), 0.f);
+                v[c * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
+                v[c * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
+              }
+              if (ns >= 32) {
+                transpose_max<5>(v, lane, 16);
+              } else if (ns == 16) {
+                transpose_max<4>(v, lane, 8);
+              } else {
+                transpose_max<3>(v, lane, 4);
+              }
+              if (ns > 32) {
+                part[(warp & 3) * 256 + c0 + lane] = v[0];
+              } else {
+                const int gg = row / ns;
+                const int nv = ns == 32 ? 1 : (ns == 16 ? 2 : 4);
+                const int cb = (lane & (ns - 1)) * nv;
+                if (gg < g_here) {
+                  const int m = m0 + gg;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (i < nv) {
+                      const int cc = c0 + cb + i;
+                      p.out[((size_t)b * cout + cc) * p.M + m] = v[i];
+                      if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cc] = v[i];
+                    }
+                  }
+                }
+              }
+            }
+          }
+          if (ns > 32) {
+            // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int wpc = ns >> 5;
+            for (int o = tid; o < G * cout; o += TP_EPI) {
+              const int gg = o / cout, cc = o - gg * cout;
+              float mx = part[(gg * wpc) * 256 + cc];
+              for (int w = 1; w < wpc; ++w) mx = fmaxf(mx, part[(gg * wpc + w) * 256 + cc]);
+              if (gg < g_here) {
+                const int m = m0 + gg;
+                p.out[((size_t)b * cout + cc) * p.M + m] = mx;
+                if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cc] = mx;
+              }
+            }
+          }
+        }
+      }
+      ++tl;
+#ifdef B200_TC_PROFILE
+      ++tp_tiles;
+#endif
+    }
+  }
+#ifdef B200_TC_PROFILE
+  if (blockIdx.x == 0 && (tid == 0 || tid == TP_PROD0 || tid == TP_MMA_WARP * 32 || tid == TP_LOAD_WARP * 32)) {
+    const int role = tid == 0 ? 3 : (tid == TP_PROD0 ? 2 : (tid == TP_MMA_WARP * 32 ? 1 : 0));
+    for (int c = 0; c < 16; ++c)
+      if (tp_acc[c]) atomicAdd(&g_tcp_prof[c], tp_acc[c]);
+    atomicAdd(&g_tcp_prof[16 + role], (unsigned long long)(clock64() - tp_start));
+    if (tid == 0) atomicAdd(&g_tcp_prof[21], tp_tiles);
+  }
+#endif
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == TP_MMA_WARP) tc::tmem_dealloc<512>(tmem_d);
+}
+
+#ifdef B200_TC_PROFILE
+extern "C" int b200_debug_tcp_profile(unsigned long long *out32) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_tcp_prof, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_tcp_prof, z, sizeof(z));
+  return 0;
+}
+#endif
+
+// Geometry + launch.  `p` carries the layer table, packed weights and row sources prepared by sa_tc_launch (sa_tc.cu).
+int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
+  static int force_slots = -1;
+  if (force_slots < 0) {
+    const char *e = getenv("B200_SA_TC_SLOTS");
+    force_slots = e ? atoi(e) : 0;
+  }
+  p.tiles_per_scene = ceil_div(p.M, p.G);
+  p.total_tiles = p.B * p.tiles_per_scene;
+  p.tile_counter = tile_counter;
+  p.final_shfl = 1;
+  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float);
+  const size_t rest = fixed + (size_t)p.r1_bytes;
+  p.nslots = (rest + 8 * (size_t)p.wslot_bytes <= 226 * 1024) ? 8 : 4;
+  if (force_slots == 4 || (force_slots == 8 && p.nslots == 8)) p.nslots = force_slots;
+  const size_t smem = rest + (size_t)p.nslots * p.wslot_bytes;
+  static size_t attr = 0;
+  if (smem > attr) {
+    B200_CUDA_OK(cudaFuncSetAttribute(sa_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  B200_CUDA_OK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), stream));
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  sa_tcp_kernel<<<grid, TP_THREADS, smem, stream>>>(p);
+  B200_LAUNCH_OK("sa_tcp_kernel");
+  return 0;
+}
+
+}  // namespace b200

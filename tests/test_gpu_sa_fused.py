@@ -78,6 +78,19 @@ def test_sa_shapes(orc, tr, pkg, shape):
     run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 1000 + N, dup=0.05)
 
 
+@pytest.mark.parametrize("shape", [
+    # more tiles than SMs: every persistent CTA walks several tiles (tile queue, weight-ring wrap-around, both TMEM
+    # accumulator sets, layer-1 stage parity across tiles)
+    (2, 9000, 1024, 1, 0.25, 64, [64, 64, 128]),     # SA1-like: 1024 tiles, odd number of layer-1 k-blocks
+    (2, 2048, 1024, 128, 0.4, 32, [128, 128, 256]),   # SA2-like: 512 tiles, 256-wide last layer (two halves)
+    (3, 1024, 700, 256, 0.8, 16, [128, 128, 128]),    # vote-aggregation-like: 264 tiles, last tile of a scene partial
+    (2, 1500, 900, 61, 0.5, 8, [32, 64]),             # nsample 8, unaligned features (scalar gather), 2 layers
+])
+def test_sa_many_tiles_per_cta(orc, tr, pkg, shape):
+    B, N, M, C, r, ns, spec = shape
+    run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 77 + M, dup=0.02)
+
+
 def test_no_xyz_and_unnormalised(orc, tr, pkg):
     run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=5, use_xyz=False, normalize=False)
     run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=6, use_xyz=True, normalize=False)

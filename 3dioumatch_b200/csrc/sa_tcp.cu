@@ -15,9 +15,13 @@
 //                          per MMA, ~150 cycles of issue per 64-cycle MMA: measured with scripts/tcp_profile.py)
 //   warp  13    loader   : tile scheduler (atomicAdd + shared-memory tile ring, one tile ahead) and the weight stream
 //                          (cp.async.bulk ring of 4 or 8 half stages, continuous across tiles)
-// TMEM: 512 columns, two accumulator sets (set s: products at 128 s, split-precision corrections at 256 + 128 s).
-// Hidden layers use set 0; the last layer uses set h for half h (256-wide outputs) or set 1 (<= 128-wide), so the
-// final epilogue of tile i runs under the layer-1 MMAs of tile i+1.
+// TMEM (512 columns) is split in two 256-column regions that swap roles every tile: one holds the accumulators
+// (products in [0,128), split-precision corrections in [128,256)), the other the hidden activations X_hi | X_lo, which
+// the epilogue writes with tcgen05.st and the next layer's MMAs read as their A operand straight from tensor memory
+// (measured: 70 cycles per 128x128x8 TF32 MMA with A in TMEM vs 86 from shared memory, scripts/tc_rate.py).  Hidden
+// activations therefore never touch shared memory: the 128 KB they used to occupy is a 4-stage ring for the layer-1
+// operand, so the gather of tile i+1 runs completely under the MMAs of tile i; and because the regions swap, the final
+// epilogue of tile i drains its accumulators while tile i+1's layer-1 MMAs already fill the other region.
 #include <stdlib.h>
 
 #include "../../include/b200_pointnet2.h"
@@ -32,7 +36,8 @@ constexpr int TP_EPI = 256;     // epilogue threads (warps 0-7)
 constexpr int TP_PROD0 = 256;   // first producer thread (warps 8-11)
 constexpr int TP_MMA_WARP = 12, TP_LOAD_WARP = 13;
 constexpr int TP_TQ = 4;        // depth of the tile-id ring
-constexpr int TP_MAXSLOTS = 8;  // weight ring slots (p.nslots = 4 or 8)
+constexpr int TP_MAXSLOTS = 8;  // weight ring slots (p.nslots = 3..8)
+constexpr int TP_ASTAGES = 4;   // layer-1 operand ring (A_hi | A_lo of one k-block per stage)
 
 // mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
@@ -72,6 +77,32 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (128 lanes x 8 columns of TF32) is read from tensor memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns: thread i of the warp writes lane (base lane + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Butterfly transpose-reduce: every lane enters with 32 column values of its own row; after STEPS exchange steps over
 // the lane bits below min(nsample, 32) each lane holds the maxima, over the nsample-lane group it belongs to, of
 // 32 >> STEPS columns:  column = ((lane & (min(ns,32) - 1)) << (5 - STEPS)) | i.
@@ -108,14 +139,14 @@ __device__ unsigned long long g_tcp_prof[32];
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *R1 = base;                                                        // layer-1 A stages / X_hi | X_lo
+  uint8_t *R1 = base;                                                        // layer-1 operand ring: TP_ASTAGES x 32 KB
   uint8_t *R2 = base + p.r1_bytes;                                           // weight ring: nslots x wslot_bytes
   float *s_scale = reinterpret_cast<float *>(R2 + p.nslots * p.wslot_bytes);  // [TC_MAXL][256]
   float *s_shift = s_scale + TC_MAXL * 256;
   float *s_partial = s_shift + TC_MAXL * 256;                                // [2][4][256] per-warp maxima (nsample > 32)
 
-  __shared__ uint64_t full_a[2], empty_a[2], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
-  __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free[2], tq_full[TP_TQ], tq_empty[TP_TQ];
+  __shared__ uint64_t full_a[TP_ASTAGES], empty_a[TP_ASTAGES], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
+  __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free, tq_full[TP_TQ], tq_empty[TP_TQ];
   __shared__ int tq_tile[TP_TQ];
   __shared__ uint32_t tmem_base_s;
 
@@ -126,12 +157,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 
   if (warp == TP_MMA_WARP) tc::tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TP_ASTAGES; ++s) {
       tc::mbar_init(&full_a[s], 128);
       tc::mbar_init(&empty_a[s], 1);
-      tc::mbar_init(&accum_half[s], 1);
-      tc::mbar_init(&d_free[s], TP_EPI);
     }
+    tc::mbar_init(&accum_half[0], 1);
+    tc::mbar_init(&accum_half[1], 1);
+    tc::mbar_init(&d_free, TP_EPI);
     for (int s = 0; s < TP_MAXSLOTS; ++s) {
       tc::mbar_init(&full_w[s], 1);
       tc::mbar_init(&empty_w[s], 1);
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       ++n_pub;
       return t;
     };
-    uint32_t i = 0;
+    uint32_t sw = 0, pw = 0;  // weight-ring slot and phase
     int cur = publish();
     while (cur >= 0) {
       const int nxt = publish();  // one tile ahead: the producers prefetch its rows while this one computes
@@ -197,94 +229,96 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         const int nst = p.L[l].nhalf * p.L[l].nkb;
         const uint8_t *src = p.packed + p.L[l].packed_off;
         const uint32_t part_bytes = (uint32_t)p.L[l].rows * 128u;  // W_hi or W_lo of one k-block
-        for (int s = 0; s < 2 * nst; ++s, ++i) {                  // packed order: hi(0), lo(0), hi(1), lo(1), ...
-          const uint32_t st = i % (uint32_t)nslots;
-          TPW(1, &empty_w[st], ((i / (uint32_t)nslots) & 1u) ^ 1u);
+        for (int s = 0; s < 2 * nst; ++s) {                       // packed order: hi(0), lo(0), hi(1), lo(1), ...
+          TPW(1, &empty_w[sw], pw ^ 1u);
           if (elect_one()) {
-            tc::mbar_arrive_expect_tx(&full_w[st], part_bytes);
-            tc::bulk_g2s(R2 + st * p.wslot_bytes, src + (size_t)s * part_bytes, part_bytes, &full_w[st]);
+            tc::mbar_arrive_expect_tx(&full_w[sw], part_bytes);
+            tc::bulk_g2s(R2 + sw * p.wslot_bytes, src + (size_t)s * part_bytes, part_bytes, &full_w[sw]);
           }
           __syncwarp();
+          if (++sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
         }
       }
       cur = nxt;
     }
   } else if (warp == TP_MMA_WARP) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
-    uint32_t i = 0, ka = 0, n_xr = 0, tl = 0;
+    uint32_t sw = 0, pw = 0, sa = 0, pa = 0, n_xr = 0, tl = 0;
     const uint32_t r1_addr = tc::smem_addr(R1), r2_addr = tc::smem_addr(R2);
     for (;;) {
       const int t = next_tile(lane == 0);
       if (t < 0) break;
+      const uint32_t d_big = tmem_d + ((tl & 1u) ? 256u : 0u);  // this tile's accumulator region
+      const uint32_t d_small = d_big + 128u;
+      const uint32_t x_hi = tmem_d + ((tl & 1u) ? 0u : 256u);   // this tile's activation region (A operand, layers >= 2)
+      const uint32_t x_lo = x_hi + 128u;
       for (int l = 0; l < nl; ++l) {
         const bool last = l == nl - 1;
         if (l > 0) {
-          TPW(3, &x_ready, n_xr & 1u);  // hidden activations of layer l-1 are in R1 (and set 0 was read)
+          TPW(3, &x_ready, n_xr & 1u);  // layer l-1's activations are in tensor memory, its accumulators were read
           ++n_xr;
           tc::tc_fence_after_sync();
         }
         const int nkb = p.L[l].nkb;
         const uint32_t idesc = tc::make_idesc_tf32(128, p.L[l].rows);
         for (int h = 0; h < p.L[l].nhalf; ++h) {
-          const int set = last ? (nhalf_last == 2 ? h : 1) : 0;
-          // write-after-read on the accumulator columns: the previous tile's final epilogue must have drained them
-          if (tl > 0) {
-            if (last && set == 1) {
-              TPW(4, &d_free[1], (tl - 1u) & 1u);
-              tc::tc_fence_after_sync();
-            } else if (l == 0 && nhalf_last == 2) {
-              TPW(4, &d_free[0], (tl - 1u) & 1u);
-              tc::tc_fence_after_sync();
-            }
+          if (last && h == 1) {  // the second half reuses the accumulator columns the epilogue is draining
+            TPW(4, &d_free, tl & 1u);
+            tc::tc_fence_after_sync();
           }
-          const uint32_t d_big = tmem_d + (uint32_t)(set * 128);
-          const uint32_t d_small = d_big + 256u;
           for (int kb = 0; kb < nkb; ++kb) {
-            uint32_t a_hi, a_lo;
+            uint64_t da_hi = 0, da_lo = 0;
             if (l == 0) {
-              const uint32_t as = ka & 1u;
-              TPW(5, &full_a[as], (ka >> 1) & 1u);
-              a_hi = r1_addr + as * 2u * TC_KB_BYTES;
-              a_lo = a_hi + TC_KB_BYTES;
-            } else {
-              a_hi = r1_addr + (uint32_t)kb * TC_KB_BYTES;
-              a_lo = a_hi + (uint32_t)p.x_lo_off;
+              TPW(5, &full_a[sa], pa);
+              const uint32_t a_hi = r1_addr + sa * 2u * TC_KB_BYTES;
+              da_hi = tc::make_desc_sw128(a_hi);
+              da_lo = tc::make_desc_sw128(a_hi + TC_KB_BYTES);
             }
-            const uint64_t da_hi = tc::make_desc_sw128(a_hi), da_lo = tc::make_desc_sw128(a_lo);
+            const uint32_t xc = (uint32_t)(kb * 32);
             {  // W_hi slot: A_hi*W_hi -> products, A_lo*W_hi -> corrections
-              const uint32_t sl = i % (uint32_t)nslots;
-              TPW(6, &full_w[sl], (i / (uint32_t)nslots) & 1u);
+              TPW(6, &full_w[sw], pw);
               tc::tc_fence_after_sync();
-              const uint64_t dw = tc::make_desc_sw128(r2_addr + sl * (uint32_t)p.wslot_bytes);
+              const uint64_t dw = tc::make_desc_sw128(r2_addr + sw * (uint32_t)p.wslot_bytes);
               if (elect_one()) {
+                if (l == 0) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
-                  tc::mma_tf32(d_big, da_hi + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                  tc::mma_tf32(d_small, da_lo + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
+                    tc::mma_tf32(d_big, da_hi + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    tc::mma_tf32(d_small, da_lo + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                  }
+                } else {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);
+                    mma_tf32_ts(d_big, x_hi + xc + (uint32_t)(ks * 8), dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    mma_tf32_ts(d_small, x_lo + xc + (uint32_t)(ks * 8), dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                  }
                 }
-                tc::mma_commit(&empty_w[sl]);
+                tc::mma_commit(&empty_w[sw]);
               }
               __syncwarp();
-              ++i;
+              if (++sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
             }
             {  // W_lo slot: A_hi*W_lo -> corrections
-              const uint32_t sl = i % (uint32_t)nslots;
-              TPW(6, &full_w[sl], (i / (uint32_t)nslots) & 1u);
+              TPW(6, &full_w[sw], pw);
               tc::tc_fence_after_sync();
-              const uint64_t dw = tc::make_desc_sw128(r2_addr + sl * (uint32_t)p.wslot_bytes);
+              const uint64_t dw = tc::make_desc_sw128(r2_addr + sw * (uint32_t)p.wslot_bytes);
               if (elect_one()) {
+                if (l == 0) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t adv = (uint64_t)(ks * 2);
-                  tc::mma_tf32(d_small, da_hi + adv, dw + adv, idesc, 1u);
+                  for (int ks = 0; ks < 4; ++ks) tc::mma_tf32(d_small, da_hi + (uint64_t)(ks * 2), dw + (uint64_t)(ks * 2), idesc, 1u);
+                  tc::mma_commit(&empty_a[sa]);
+                } else {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    mma_tf32_ts(d_small, x_hi + xc + (uint32_t)(ks * 8), dw + (uint64_t)(ks * 2), idesc, 1u);
                 }
-                if (l == 0) tc::mma_commit(&empty_a[ka & 1u]);
-                tc::mma_commit(&empty_w[sl]);
+                tc::mma_commit(&empty_w[sw]);
               }
               __syncwarp();
-              if (l == 0) ++ka;
-              ++i;
+              if (l == 0 && ++sa == (uint32_t)TP_ASTAGES) { sa = 0; pa ^= 1u; }
+              if (++sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
             }
           }
           if (last) {
@@ -304,7 +338,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     const int row = tid - TP_PROD0;
     const int g = row / ns;
     const int C = p.C;
-    uint32_t ka = 0, tl = 0;
+    uint32_t sa = 0, pa = 0;
     for (;;) {
       const int t = next_tile(true);
       if (t < 0) break;
@@ -377,9 +411,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         }
       };
       auto store_kb = [&](const float4 (&v)[8]) {
-        const uint32_t as = ka & 1u;
-        TPW(9, &empty_a[as], ((ka >> 1) & 1u) ^ 1u);
-        uint8_t *a_hi = R1 + as * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
+        TPW(9, &empty_a[sa], pa ^ 1u);
+        uint8_t *a_hi = R1 + sa * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 h, l;
@@ -390,72 +423,69 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           *reinterpret_cast<float4 *>(a_lo + off) = l;
         }
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&full_a[as]);
-        ++ka;
+        tc::mbar_arrive(&full_a[sa]);
+        if (++sa == (uint32_t)TP_ASTAGES) { sa = 0; pa ^= 1u; }
       };
+      // register double buffer: the loads of k-block kb+1 are in flight while kb is split and stored; the operand ring
+      // is private to layer 1, so the whole gather runs ahead of the MMAs (up to TP_ASTAGES k-blocks)
       const int nkb1 = p.L[0].nkb;
       float4 va[8], vb[8];
-      load_kb(0, va);  // both in flight while the previous tile still computes
-      if (nkb1 > 1) load_kb(1, vb);
-      if (tl > 0) {
-        // R1 doubles as the hidden activations of the previous tile: wait until its last MMA has read them
-        TPW(10, &accum_half[nhalf_last - 1], (tl - 1u) & 1u);
-      }
+      load_kb(0, va);
       for (int kb = 0; kb < nkb1; kb += 2) {
+        if (kb + 1 < nkb1) load_kb(kb + 1, vb);
         store_kb(va);
-        if (kb + 2 < nkb1) load_kb(kb + 2, va);
         if (kb + 1 < nkb1) {
+          if (kb + 2 < nkb1) load_kb(kb + 2, va);
           store_kb(vb);
-          if (kb + 3 < nkb1) load_kb(kb + 3, vb);
         }
       }
-      ++tl;
     }
   } else {
     // ================= epilogue: warpgroup wg takes the 32-column chunks wg, wg+2, ...; row = TMEM lane =================
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     uint32_t n_acc = 0, tl = 0;
-    const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     for (;;) {
       const int t = next_tile(true);
       if (t < 0) break;
       const int b = t / p.tiles_per_scene;
       const int m0 = (t - b * p.tiles_per_scene) * G;
       const int g_here = min(G, p.M - m0);
+      const uint32_t d_addr = lane_base + ((tl & 1u) ? 256u : 0u);  // accumulators: products | corrections (+128)
+      const uint32_t x_addr = lane_base + ((tl & 1u) ? 0u : 256u);  // activations:  X_hi | X_lo (+128)
       for (int l = 0; l < nl; ++l) {
         const float *sc = s_scale + l * 256, *sh = s_shift + l * 256;
         if (l + 1 < nl) {
           TPW(13, &accum_full, n_acc & 1u);
           ++n_acc;
           tc::tc_fence_after_sync();
-          // hidden layer: X = relu(scale*acc+shift) -> split -> R1 as the next layer's K-major operand (set 0)
-          uint8_t *x_hi = R1, *x_lo = R1 + p.x_lo_off;
+          // hidden layer: X = relu(scale*acc+shift) -> hi/lo split -> tensor memory (the next layer's A operand)
           const int H = p.L[l].cout;  // hidden width, multiple of 32
           for (int c0 = wg * 32; c0 < H; c0 += 64) {
             uint32_t r[32], r2[32];
-            tc::tmem_ld_32x32(lane_addr + (uint32_t)c0, r);
-            tc::tmem_ld_32x32(lane_addr + 256u + (uint32_t)c0, r2);
+            tc::tmem_ld_32x32(d_addr + (uint32_t)c0, r);
+            tc::tmem_ld_32x32(d_addr + 128u + (uint32_t)c0, r2);
             tc::tmem_ld_wait();
-            uint8_t *kb_hi = x_hi + (c0 >> 5) * TC_KB_BYTES, *kb_lo = x_lo + (c0 >> 5) * TC_KB_BYTES;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
               const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
               const float scv[4] = {s4.x, s4.y, s4.z, s4.w}, shv[4] = {h4.x, h4.y, h4.z, h4.w};
-              float y[4], hh[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float acc = __uint_as_float(r[c * 4 + e]) + __uint_as_float(r2[c * 4 + e]);
-                y[e] = fmaxf(fmaf(acc, scv[e], shv[e]), 0.f);
-                tc::split_tf32(y[e], hh[e], lo[e]);
+                const float y = fmaxf(fmaf(acc, scv[e], shv[e]), 0.f);
+                float hh, lo;
+                tc::split_tf32(y, hh, lo);
+                r[c * 4 + e] = __float_as_uint(hh);
+                r2[c * 4 + e] = __float_as_uint(lo);
               }
-              const uint32_t off = tc::sw128_offset(row, c);
-              *reinterpret_cast<float4 *>(kb_hi + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<float4 *>(kb_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
+            tmem_st_32x32(x_addr + (uint32_t)c0, r);
+            tmem_st_32x32(x_addr + 128u + (uint32_t)c0, r2);
           }
-          tc::fence_proxy_async_smem();
+          tmem_st_wait();
           tc::tc_fence_before_sync();
           tc::mbar_arrive(&x_ready);
         } else {
@@ -465,23 +495,22 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           const int rows_l = p.L[l].rows;
           float *part = s_partial + (tl & 1u) * (4 * 256);
           for (int h = 0; h < nhalf_last; ++h) {
-            const int set = nhalf_last == 2 ? h : 1;
             TPW(14, &accum_half[h], tl & 1u);
             tc::tc_fence_after_sync();
-            const uint32_t set_addr = lane_addr + (uint32_t)(set * 128);
-            if (wg * 32 >= rows_l) {  // no chunk for this warpgroup in this half: it has nothing to drain
+            const bool release = nhalf_last == 2 && h == 0;  // half 1 accumulates into the same columns
+            if (release && wg * 32 >= rows_l) {              // no chunk for this warpgroup: nothing to drain
               tc::tc_fence_before_sync();
-              tc::mbar_arrive(&d_free[set]);
+              tc::mbar_arrive(&d_free);
             }
             for (int cc0 = wg * 32; cc0 < rows_l; cc0 += 64) {
               const int c0 = h * rows_l + cc0;  // output channel of the chunk's first column
               uint32_t r[32], r2[32];
-              tc::tmem_ld_32x32(set_addr + (uint32_t)cc0, r);
-              tc::tmem_ld_32x32(set_addr + 256u + (uint32_t)cc0, r2);
+              tc::tmem_ld_32x32(d_addr + (uint32_t)cc0, r);
+              tc::tmem_ld_32x32(d_addr + 128u + (uint32_t)cc0, r2);
               tc::tmem_ld_wait();
-              if (cc0 + 64 >= rows_l) {  // this thread's last read of the set: the MMA warp may overwrite it (next tile)
+              if (release && cc0 + 64 >= rows_l) {  // this thread's last read of half 0
                 tc::tc_fence_before_sync();
-                tc::mbar_arrive(&d_free[set]);
+                tc::mbar_arrive(&d_free);
               }
               float v[32];
 #pragma unroll
@@ -579,9 +608,13 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float);
+  p.r1_bytes = TP_ASTAGES * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
-  p.nslots = (rest + 8 * (size_t)p.wslot_bytes <= 226 * 1024) ? 8 : 4;
-  if (force_slots == 4 || (force_slots == 8 && p.nslots == 8)) p.nslots = force_slots;
+  const size_t budget = 227 * 1024 - 512;          // dynamic + the kernel's static shared memory
+  int slots = (int)((budget - rest) / (size_t)p.wslot_bytes);
+  p.nslots = slots > TP_MAXSLOTS ? TP_MAXSLOTS : slots;
+  if (force_slots >= 2 && force_slots < p.nslots) p.nslots = force_slots;
+  B200_CHECK_ARG(p.nslots >= 2, "sa_forward(tc): weight ring does not fit (%d-byte slots)", p.wslot_bytes);
   const size_t smem = rest + (size_t)p.nslots * p.wslot_bytes;
   static size_t attr = 0;
   if (smem > attr) {

@@ -38,7 +38,7 @@ struct TcParams {
   int cluster;       // 2: CTA pairs share every weight stage through one multicast bulk copy (half the L2 reads)
   int mode;
   // persistent kernel (sa_tcp_kernel): weight-ring depth, tile queue
-  int nslots, total_tiles, tiles_per_scene;
+  int nslots, a_stages, total_tiles, tiles_per_scene;
   int final_shfl;  // 1: final max-reduce by warp shuffles (no slab, no CTA barriers per chunk)
   int *tile_counter;
   const int32_t *idx3;   // (B, M*ns, 3)

@@ -37,7 +37,7 @@ constexpr int TP_PROD0 = 256;   // first producer thread (warps 8-11)
 constexpr int TP_MMA_WARP = 12, TP_LOAD_WARP = 13;
 constexpr int TP_TQ = 4;        // depth of the tile-id ring
 constexpr int TP_MAXSLOTS = 8;  // weight ring slots (p.nslots = 3..8)
-constexpr int TP_ASTAGES = 4;   // layer-1 operand ring (A_hi | A_lo of one k-block per stage)
+constexpr int TP_ASTAGES = 4;   // layer-1 operand ring: at most this many stages (A_hi | A_lo of one k-block each)
 
 // mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
@@ -125,15 +125,35 @@ __device__ __forceinline__ void transpose_max(float (&v)[32], int lane, int top_
 }
 
 #ifdef B200_TC_PROFILE
-__device__ unsigned long long g_tcp_prof[32];
+__device__ unsigned long long g_tcp_prof[48];
 #define TPW(cat, bar, par)                                \
   do {                                                    \
     const long long _w0 = clock64();                      \
     mbar_wait_wd(bar, par);                               \
     tp_acc[cat] += (unsigned long long)(clock64() - _w0); \
   } while (0)
+#define TP_BEGIN() long long _r0 = clock64()
+#define TP_END(cat) tp_acc[cat] += (unsigned long long)(clock64() - _r0)
+#define TP_HBEGIN() long long _h0 = clock64()
+#define TP_HLAP(cat)                                       \
+  do {                                                     \
+    const long long _n = clock64();                        \
+    tp_acc[cat] += (unsigned long long)(_n - _h0);         \
+    _h0 = _n;                                              \
+  } while (0)
+#define TP_LAP(cat)                                        \
+  do {                                                     \
+    const long long _n = clock64();                        \
+    tp_acc[cat] += (unsigned long long)(_n - _r0);         \
+    _r0 = _n;                                              \
+  } while (0)
 #else
 #define TPW(cat, bar, par) mbar_wait_wd(bar, par)
+#define TP_BEGIN()
+#define TP_END(cat)
+#define TP_LAP(cat)
+#define TP_HBEGIN()
+#define TP_HLAP(cat)
 #endif
 
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   tc::tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
 #ifdef B200_TC_PROFILE
-  unsigned long long tp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tp_acc[32] = {0};
   const int tp_tile_cat = warp == TP_MMA_WARP ? 2 : (warp >= 8 ? 8 : 12);
   const long long tp_start = clock64();
   unsigned long long tp_tiles = 0;
@@ -268,58 +288,60 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           }
           for (int kb = 0; kb < nkb; ++kb) {
             uint64_t da_hi = 0, da_lo = 0;
+            int nks = 4;  // UMMA_K = 8 columns per MMA; a partially filled last layer-1 k-block needs fewer steps
             if (l == 0) {
               TPW(5, &full_a[sa], pa);
               const uint32_t a_hi = r1_addr + sa * 2u * TC_KB_BYTES;
               da_hi = tc::make_desc_sw128(a_hi);
               da_lo = tc::make_desc_sw128(a_hi + TC_KB_BYTES);
+              if (kb == nkb - 1) nks = (p.L[0].cin - kb * 32 + 7) >> 3;
             }
             const uint32_t xc = (uint32_t)(kb * 32);
-            {  // W_hi slot: A_hi*W_hi -> products, A_lo*W_hi -> corrections
-              TPW(6, &full_w[sw], pw);
-              tc::tc_fence_after_sync();
-              const uint64_t dw = tc::make_desc_sw128(r2_addr + sw * (uint32_t)p.wslot_bytes);
-              if (elect_one()) {
-                if (l == 0) {
+            // both halves of the k-block's weights (W_hi in slot sw, W_lo in the next slot), then ONE issue burst:
+            //   A_hi*W_hi -> products, A_lo*W_hi -> corrections, A_hi*W_lo -> corrections
+            uint32_t sw2 = sw + 1, pw2 = pw;
+            if (sw2 == (uint32_t)nslots) { sw2 = 0; pw2 ^= 1u; }
+            TPW(6, &full_w[sw], pw);
+            TPW(6, &full_w[sw2], pw2);
+            tc::tc_fence_after_sync();
+            TP_BEGIN();
+            const uint64_t dwh = tc::make_desc_sw128(r2_addr + sw * (uint32_t)p.wslot_bytes);
+            const uint64_t dwl = tc::make_desc_sw128(r2_addr + sw2 * (uint32_t)p.wslot_bytes);
+            if (elect_one()) {
+              if (l == 0) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < nks) {
                     const uint64_t adv = (uint64_t)(ks * 2);  // 8 floats = 32 B = 2 x 16 B
-                    tc::mma_tf32(d_big, da_hi + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                    tc::mma_tf32(d_small, da_lo + adv, dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                  }
-                } else {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);
-                    mma_tf32_ts(d_big, x_hi + xc + (uint32_t)(ks * 8), dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                    mma_tf32_ts(d_small, x_lo + xc + (uint32_t)(ks * 8), dw + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    tc::mma_tf32(d_big, da_hi + adv, dwh + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    tc::mma_tf32(d_small, da_lo + adv, dwh + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
                   }
                 }
                 tc::mma_commit(&empty_w[sw]);
-              }
-              __syncwarp();
-              if (++sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
-            }
-            {  // W_lo slot: A_hi*W_lo -> corrections
-              TPW(6, &full_w[sw], pw);
-              tc::tc_fence_after_sync();
-              const uint64_t dw = tc::make_desc_sw128(r2_addr + sw * (uint32_t)p.wslot_bytes);
-              if (elect_one()) {
-                if (l == 0) {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) tc::mma_tf32(d_small, da_hi + (uint64_t)(ks * 2), dw + (uint64_t)(ks * 2), idesc, 1u);
-                  tc::mma_commit(&empty_a[sa]);
-                } else {
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks) tc::mma_tf32(d_small, da_hi + (uint64_t)(ks * 2), dwl + (uint64_t)(ks * 2), idesc, 1u);
+                tc::mma_commit(&empty_a[sa]);
+                tc::mma_commit(&empty_w[sw2]);
+              } else {
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    mma_tf32_ts(d_small, x_hi + xc + (uint32_t)(ks * 8), dw + (uint64_t)(ks * 2), idesc, 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);
+                  mma_tf32_ts(d_big, x_hi + xc + (uint32_t)(ks * 8), dwh + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                  mma_tf32_ts(d_small, x_lo + xc + (uint32_t)(ks * 8), dwh + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
                 }
                 tc::mma_commit(&empty_w[sw]);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_tf32_ts(d_small, x_hi + xc + (uint32_t)(ks * 8), dwl + (uint64_t)(ks * 2), idesc, 1u);
+                tc::mma_commit(&empty_w[sw2]);
               }
-              __syncwarp();
-              if (l == 0 && ++sa == (uint32_t)TP_ASTAGES) { sa = 0; pa ^= 1u; }
-              if (++sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
             }
+            __syncwarp();
+            TP_END(7);
+            if (l == 0 && ++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1u; }
+            sw = sw2 + 1; pw = pw2;
+            if (sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
           }
           if (last) {
             if (elect_one()) tc::mma_commit(&accum_half[h]);
@@ -424,7 +446,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&full_a[sa]);
-        if (++sa == (uint32_t)TP_ASTAGES) { sa = 0; pa ^= 1u; }
+        if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1u; }
       };
       // register double buffer: the loads of k-block kb+1 are in flight while kb is split and stored; the operand ring
       // is private to layer 1, so the whole gather runs ahead of the MMAs (up to TP_ASTAGES k-blocks)
@@ -460,13 +482,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           TPW(13, &accum_full, n_acc & 1u);
           ++n_acc;
           tc::tc_fence_after_sync();
+          TP_BEGIN();
           // hidden layer: X = relu(scale*acc+shift) -> hi/lo split -> tensor memory (the next layer's A operand)
           const int H = p.L[l].cout;  // hidden width, multiple of 32
           for (int c0 = wg * 32; c0 < H; c0 += 64) {
             uint32_t r[32], r2[32];
+            TP_HBEGIN();
             tc::tmem_ld_32x32(d_addr + (uint32_t)c0, r);
             tc::tmem_ld_32x32(d_addr + 128u + (uint32_t)c0, r2);
             tc::tmem_ld_wait();
+            TP_HLAP(20);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
@@ -482,12 +507,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 r2[c * 4 + e] = __float_as_uint(lo);
               }
             }
+            TP_HLAP(21);
             tmem_st_32x32(x_addr + (uint32_t)c0, r);
             tmem_st_32x32(x_addr + 128u + (uint32_t)c0, r2);
           }
           tmem_st_wait();
           tc::tc_fence_before_sync();
           tc::mbar_arrive(&x_ready);
+          TP_END(15);
         } else {
           // last layer: relu(scale*acc+shift), then the max over each centre's nsample rows.  Rows are TMEM lanes =
           // lanes of this warp (and of its neighbours when nsample > 32): reduce in registers with warp shuffles.
@@ -505,9 +532,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             for (int cc0 = wg * 32; cc0 < rows_l; cc0 += 64) {
               const int c0 = h * rows_l + cc0;  // output channel of the chunk's first column
               uint32_t r[32], r2[32];
+              TP_BEGIN();
               tc::tmem_ld_32x32(d_addr + (uint32_t)cc0, r);
               tc::tmem_ld_32x32(d_addr + 128u + (uint32_t)cc0, r2);
               tc::tmem_ld_wait();
+              TP_LAP(16);
               if (release && cc0 + 64 >= rows_l) {  // this thread's last read of half 0
                 tc::tc_fence_before_sync();
                 tc::mbar_arrive(&d_free);
@@ -529,6 +558,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               } else {
                 transpose_max<3>(v, lane, 4);
               }
+              TP_LAP(17);
               if (ns > 32) {
                 part[(warp & 3) * 256 + c0 + lane] = v[0];
               } else {
@@ -547,9 +577,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                   }
                 }
               }
+              TP_LAP(18);
             }
           }
           if (ns > 32) {
+            TP_BEGIN();
             // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int wpc = ns >> 5;
@@ -563,6 +595,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 if (p.out_pm) p.out_pm[((size_t)b * p.M + m) * cout + cc] = mx;
               }
             }
+            TP_END(19);
           }
         }
       }
@@ -575,8 +608,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 #ifdef B200_TC_PROFILE
   if (blockIdx.x == 0 && (tid == 0 || tid == TP_PROD0 || tid == TP_MMA_WARP * 32 || tid == TP_LOAD_WARP * 32)) {
     const int role = tid == 0 ? 3 : (tid == TP_PROD0 ? 2 : (tid == TP_MMA_WARP * 32 ? 1 : 0));
-    for (int c = 0; c < 16; ++c)
-      if (tp_acc[c]) atomicAdd(&g_tcp_prof[c], tp_acc[c]);
+    for (int c = 0; c < 32; ++c)
+      if (tp_acc[c]) atomicAdd(&g_tcp_prof[c < 16 ? c : c + 8], tp_acc[c]);
     atomicAdd(&g_tcp_prof[16 + role], (unsigned long long)(clock64() - tp_start));
     if (tid == 0) atomicAdd(&g_tcp_prof[21], tp_tiles);
   }
@@ -589,8 +622,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 #ifdef B200_TC_PROFILE
 extern "C" int b200_debug_tcp_profile(unsigned long long *out32) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out32, g_tcp_prof, sizeof(unsigned long long) * 32);
-  unsigned long long z[32] = {0};
+  cudaMemcpyFromSymbol(out32, g_tcp_prof, sizeof(unsigned long long) * 48);
+  unsigned long long z[48] = {0};
   cudaMemcpyToSymbol(g_tcp_prof, z, sizeof(z));
   return 0;
 }
@@ -608,7 +641,13 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float);
-  p.r1_bytes = TP_ASTAGES * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
+  static int force_astages = -1;
+  if (force_astages < 0) {
+    const char *e = getenv("B200_SA_TC_ASTAGES");
+    force_astages = e ? atoi(e) : 0;
+  }
+  p.a_stages = (force_astages >= 2 && force_astages <= TP_ASTAGES) ? force_astages : 3;
+  p.r1_bytes = p.a_stages * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
   const size_t budget = 227 * 1024 - 512;          // dynamic + the kernel's static shared memory
   int slots = (int)((budget - rest) / (size_t)p.wslot_bytes);

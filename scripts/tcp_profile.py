@@ -9,7 +9,7 @@ pkg = importlib.import_module("3dioumatch_b200"); pkg.install_dropin()
 import pointnet2._ext as ext
 L = ctypes.CDLL(os.environ["B200_LIB_PATH"])
 cats = {0: "ldr:tq_empty", 1: "ldr:empty_w", 2: "mma:tile", 3: "mma:x_ready", 4: "mma:d_free", 5: "mma:full_a", 6: "mma:full_w",
-        8: "prod:tile", 9: "prod:empty_a", 10: "prod:r1_free", 12: "epi:tile", 13: "epi:accum_full", 14: "epi:accum_half",
+        8: "prod:tile", 9: "prod:empty_a", 7: "mma:issue W_hi groups", 10: "prod:r1_free", 15: "epi:hidden body", 24: "epi:final ld", 25: "epi:final math+shfl", 26: "epi:final store", 27: "epi:combine", 28: "epi:hidden ld", 29: "epi:hidden math", 12: "epi:tile", 13: "epi:accum_full", 14: "epi:accum_half",
         16: "TOTAL loader", 17: "TOTAL mma", 18: "TOTAL producer", 19: "TOTAL epilogue"}
 cfgs = [(8, 40000, 2048, 1, 0.2, 64, [4, 64, 64, 128]), (8, 2048, 1024, 128, 0.4, 32, [131, 128, 128, 256]),
         (8, 1024, 512, 256, 0.8, 16, [259, 128, 128, 256]), (8, 1024, 256, 256, 0.3, 16, [259, 128, 128, 128])]
@@ -22,7 +22,7 @@ for (B, N, M, C, r, ns, spec) in cfgs:
               for l in cases.mlp_params(0, spec)]
     idx = ext.ball_query(new_xyz, xyz, r, ns)
     fpm = feats.transpose(1, 2).contiguous()
-    buf = (ctypes.c_ulonglong * 32)()
+    buf = (ctypes.c_ulonglong * 48)()
     for _ in range(2):
         ext.sa_forward(xyz, None, new_xyz, r, ns, layers, normalize_xyz=True, idx=idx, features_pm=fpm)
     L.b200_debug_tcp_profile(buf)

@@ -556,14 +556,16 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   }
   uint8_t *packed = nullptr;
   const size_t counter_off = (off + 255) & ~(size_t)255;
-  B200_CUDA_OK(scratch_alloc((void **)&packed, counter_off + 256, stream));
+  const size_t unit_bytes = (persist && !idx3) ? sa_tcp_unit_scratch_bytes(B, M, nsample) : 0;
+  B200_CUDA_OK(scratch_alloc((void **)&packed, counter_off + 256 + unit_bytes, stream));
   tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
   p.nslots = 4; p.total_tiles = 0; p.tiles_per_scene = 0; p.tile_counter = nullptr; p.final_shfl = 0;
   if (persist) {
     // persistent warp-specialised kernel (sa_tcp.cu): one CTA per SM, tiles from an atomic queue
-    const int rc = sa_tcp_launch(p, reinterpret_cast<int *>(packed + counter_off), stream);
+    const int rc = sa_tcp_launch(p, reinterpret_cast<int *>(packed + counter_off),
+                                 unit_bytes ? reinterpret_cast<int *>(packed + counter_off + 256) : nullptr, stream);
     if (rc != 0) return rc;
     B200_CUDA_OK(cudaFreeAsync(packed, stream));
     return 0;

@@ -41,6 +41,11 @@ struct TcParams {
   int nslots, a_stages, total_tiles, tiles_per_scene;
   int final_shfl;  // 1: final max-reduce by warp shuffles (no slab, no CTA barriers per chunk)
   int *tile_counter;
+  // compacted mode (sa_tcp.cu): tiles are 8 units of 16 neighbour slots; a centre only contributes the units that
+  // hold distinct neighbours (the ball query pads a short list with copies of its first hit: ball_query_gpu.cu:40-46)
+  const int *unit_list;    // unit u -> centre * 8 + first slot / 16
+  const int *total_units;  // device scalar written by sa_units_kernel
+  int units;               // 1: compacted mode
   const int32_t *idx3;   // (B, M*ns, 3)
   const float *w3;       // (B, M*ns, 3)
   const float *rel3;     // (B, M*ns, 3) or NULL
@@ -49,6 +54,7 @@ struct TcParams {
 
 
 // sa_tcp.cu: launches the persistent kernel on a fully prepared parameter block (weights already packed)
-int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream);
+int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_t stream);
+size_t sa_tcp_unit_scratch_bytes(int B, int M, int nsample);
 
 }  // namespace b200

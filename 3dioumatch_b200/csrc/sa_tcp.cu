@@ -124,6 +124,68 @@ __device__ __forceinline__ void transpose_max(float (&v)[32], int lane, int top_
   }
 }
 
+
+// ---- compacted tiles: which 16-slot units of each centre hold distinct neighbours -----------------------------------
+// The reference's ball query pads a neighbour list shorter than nsample with copies of its first hit
+// (ball_query_gpu.cu:40-46), and max() over duplicated rows is the max over the distinct ones, so only the slots up
+// to the last one that differs from slot 0 need to go through the MLP (true for any index list, padded or not).
+// sa_unit_count_kernel: per centre the number of 16-slot units (one warp per centre); sa_unit_scan_kernel: exclusive
+// scan over all B*M centres and the unit list (unit -> centre * 8 + unit-in-centre) the persistent kernel's producers
+// walk.  total[0] = number of units.
+__global__ void __launch_bounds__(256) sa_unit_count_kernel(int centres, int ns, const int32_t *__restrict__ idx,
+                                                           int *__restrict__ units) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per centre, coalesced row
+  if (c >= centres) return;
+  const int32_t *row = idx + (size_t)c * ns;
+  const int32_t first = row[0];
+  int last_diff = 0;
+  for (int t0 = 0; t0 < ns; t0 += 32) {
+    const int t = t0 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, t < ns && row[t] != first);
+    if (m) last_diff = t0 + 31 - __clz(m);
+  }
+  if (lane == 0) units[c] = (last_diff >> 4) + 1;
+}
+
+__global__ void __launch_bounds__(1024) sa_unit_scan_kernel(int centres, const int *__restrict__ units_in,
+                                                           int *__restrict__ unit_list, int *__restrict__ total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_chunk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < centres; c0 += 1024) {
+    const int c = c0 + tid;
+    const int units = c < centres ? units_in[c] : 0;
+    int incl = units;  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 32 warp totals
+      const int w = s_warp[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += v;
+      }
+      s_warp[lane] = wi - w;
+      if (lane == 31) s_chunk = wi;
+    }
+    __syncthreads();
+    const int base = s_base + s_warp[warp] + (incl - units);
+    for (int u = 0; u < units; ++u) unit_list[base + u] = c * 8 + u;
+    __syncthreads();
+    if (tid == 0) s_base += s_chunk;
+    __syncthreads();
+  }
+  if (tid == 0) total[0] = s_base;
+}
+
 #ifdef B200_TC_PROFILE
 __device__ unsigned long long g_tcp_prof[48];
 #define TPW(cat, bar, par)                                \
@@ -227,13 +289,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   if (warp == TP_LOAD_WARP) {
     // ================= tile scheduler + weight loader (converged warp, elected lane issues) =================
     int n_pub = 0;
+    const int total_tiles = p.units ? (__ldg(p.total_units) + 7) >> 3 : p.total_tiles;
     auto publish = [&]() -> int {
       const int slot = n_pub % TP_TQ;
       TPW(0, &tq_empty[slot], (uint32_t)(((n_pub / TP_TQ) & 1) ^ 1));
       int t = 0;
       if (lane == 0) {
         t = atomicAdd(p.tile_counter, 1);
-        if (t >= p.total_tiles) t = -1;
+        if (t >= total_tiles) t = -1;
         tq_tile[slot] = t;
         tc::mbar_arrive(&tq_full[slot]);  // release: the tile id is visible to the waiters
       }
@@ -364,15 +427,32 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     for (;;) {
       const int t = next_tile(true);
       if (t < 0) break;
-      const int b = t / p.tiles_per_scene;
-      const int m0 = (t - b * p.tiles_per_scene) * G;
-      const int g_here = min(G, p.M - m0);
-      const bool valid = g < g_here;
+      int b, m0, g_here, slot, gi;
+      bool valid;
+      if (p.units) {
+        // compacted tile: 8 units of 16 slots, each from the centre the unit list names
+        const int u = t * 8 + (row >> 4);
+        valid = u < __ldg(p.total_units);
+        const int e = valid ? __ldg(p.unit_list + u) : 0;
+        const int c = e >> 3;
+        b = c / p.M;
+        m0 = c - b * p.M;
+        gi = 0;
+        g_here = 1;
+        slot = (e & 7) * 16 + (row & 15);
+      } else {
+        b = t / p.tiles_per_scene;
+        m0 = (t - b * p.tiles_per_scene) * G;
+        g_here = min(G, p.M - m0);
+        valid = g < g_here;
+        gi = g;
+        slot = row - g * ns;
+      }
       int src_idx = 0;
       float ctr[3] = {0.f, 0.f, 0.f};
       if (valid && p.mode == 0) {
-        src_idx = p.idx[((size_t)b * p.M + m0 + g) * ns + (row - g * ns)];
-        const float *c = p.new_xyz + ((size_t)b * p.M + m0 + g) * 3;
+        src_idx = p.idx[((size_t)b * p.M + m0 + gi) * ns + slot];
+        const float *c = p.new_xyz + ((size_t)b * p.M + m0 + gi) * 3;
         ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
       }
       const float *frow = (valid && C > 0 && p.mode == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
@@ -380,7 +460,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       const float *f3[3] = {nullptr, nullptr, nullptr};
       float wt[3] = {0.f, 0.f, 0.f};
       if (p.mode == 1 && valid) {
-        const size_t q = ((size_t)b * p.M + m0 + g) * ns + (row - g * ns);
+        const size_t q = ((size_t)b * p.M + m0 + gi) * ns + slot;
         for (int u = 0; u < 3; ++u) {
           f3[u] = p.feat_pm + ((size_t)b * p.N + p.idx3[q * 3 + u]) * C;
           wt[u] = p.w3[q * 3 + u];
@@ -471,9 +551,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     for (;;) {
       const int t = next_tile(true);
       if (t < 0) break;
-      const int b = t / p.tiles_per_scene;
-      const int m0 = (t - b * p.tiles_per_scene) * G;
-      const int g_here = min(G, p.M - m0);
+      int b = 0, m0 = 0, g_here = 0;
+      int u_centre = -1;  // compacted mode: the centre of this lane's 16-row unit (-1: past the end)
+      if (p.units) {
+        const int u = t * 8 + (row >> 4);
+        if (u < __ldg(p.total_units)) u_centre = __ldg(p.unit_list + u) >> 3;
+      } else {
+        b = t / p.tiles_per_scene;
+        m0 = (t - b * p.tiles_per_scene) * G;
+        g_here = min(G, p.M - m0);
+      }
       const uint32_t d_addr = lane_base + ((tl & 1u) ? 256u : 0u);  // accumulators: products | corrections (+128)
       const uint32_t x_addr = lane_base + ((tl & 1u) ? 0u : 256u);  // activations:  X_hi | X_lo (+128)
       for (int l = 0; l < nl; ++l) {
@@ -551,6 +638,25 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 v[c * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
                 v[c * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
               }
+              if (p.units) {
+                // 16-row units: lanes 0-15 / 16-31 reduce separately; a centre's units meet in global memory through an
+                // integer atomicMax (outputs are >= 0 after the ReLU, so the int order is the float order; the
+                // launcher zero-fills the outputs, and max is order-independent -> still bit-exact)
+                transpose_max<4>(v, lane, 8);
+                if (u_centre >= 0) {
+                  const int ub = u_centre / p.M, um = u_centre - ub * p.M;
+                  const int cb = (lane & 15) * 2;
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    const int cc = c0 + cb + i;
+                    atomicMax(reinterpret_cast<int *>(p.out + ((size_t)ub * cout + cc) * p.M + um), __float_as_int(v[i]));
+                    if (p.out_pm)
+                      atomicMax(reinterpret_cast<int *>(p.out_pm + ((size_t)ub * p.M + um) * cout + cc), __float_as_int(v[i]));
+                  }
+                }
+                TP_LAP(18);
+                continue;
+              }
               if (ns >= 32) {
                 transpose_max<5>(v, lane, 16);
               } else if (ns == 16) {
@@ -580,7 +686,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               TP_LAP(18);
             }
           }
-          if (ns > 32) {
+          if (ns > 32 && !p.units) {
             TP_BEGIN();
             // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -630,11 +736,35 @@ extern "C" int b200_debug_tcp_profile(unsigned long long *out32) {
 #endif
 
 // Geometry + launch.  `p` carries the layer table, packed weights and row sources prepared by sa_tc_launch (sa_tc.cu).
-int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
-  static int force_slots = -1;
+size_t sa_tcp_unit_scratch_bytes(int B, int M, int nsample) {
+  return ((size_t)B * M * (size_t)(nsample / 16 + 2) + 64) * sizeof(int);
+}
+
+int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_t stream) {
+  static int force_slots = -1, compact_rows = -1;
   if (force_slots < 0) {
     const char *e = getenv("B200_SA_TC_SLOTS");
     force_slots = e ? atoi(e) : 0;
+    e = getenv("B200_SA_TC_UNITS");
+    compact_rows = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  // compacted tiles: neighbour lists from a ball query, nsample 32..128 in whole 16-slot units, <= 8 units per centre
+  p.units = (compact_rows && unit_scratch && p.mode == 0 && p.ns >= 32 && (p.ns & 15) == 0 && p.ns <= 128 &&
+             (long long)p.B * p.M < (1ll << 27)) ? 1 : 0;
+  p.unit_list = nullptr;
+  p.total_units = nullptr;
+  if (p.units) {
+    const int centres = p.B * p.M;
+    int *units = unit_scratch + 64, *list = units + centres;  // [total | per-centre unit counts | unit list]
+    p.total_units = unit_scratch;
+    p.unit_list = list;
+    sa_unit_count_kernel<<<ceil_div(centres, 8), 256, 0, stream>>>(centres, p.ns, p.idx, units);
+    B200_LAUNCH_OK("sa_unit_count_kernel");
+    sa_unit_scan_kernel<<<1, 1024, 0, stream>>>(centres, units, list, unit_scratch);
+    B200_LAUNCH_OK("sa_unit_scan_kernel");
+    const int cout = p.L[p.nl - 1].cout;
+    B200_CUDA_OK(cudaMemsetAsync(p.out, 0, (size_t)p.B * cout * p.M * sizeof(float), stream));
+    if (p.out_pm) B200_CUDA_OK(cudaMemsetAsync(p.out_pm, 0, (size_t)p.B * cout * p.M * sizeof(float), stream));
   }
   p.tiles_per_scene = ceil_div(p.M, p.G);
   p.total_tiles = p.B * p.tiles_per_scene;

@@ -263,12 +263,12 @@ def make_model(ops, seed=1, num_proposal=256, device="cuda"):
     return net.to(device).eval()
 
 
-def make_inputs(B=8, N=40000, G=64, seed=0):
+def make_inputs(B=8, N=40000, G=64, seed=0, room=(8.0, 8.0, 3.0)):
     """ScanNet-shaped synthetic scenes (tests/cases.py:scene_cloud) + 64-slot padded GT boxes (numpy, host)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "tests"))
     import cases
-    pc = cases.scene_cloud(seed, B, N)
+    pc = cases.scene_cloud(seed, B, N, room=room)
     gt = np.zeros((B, G, 7), np.float32)
     rng = np.random.default_rng(seed + 100)
     for b in range(B):

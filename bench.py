@@ -35,12 +35,14 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref", action="store_true", help="skip the in-run timing of the reference CUDA ops")
     ap.add_argument("--no-breakdown", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3,
+    ap.add_argument("--lanes", type=int, default=5,
                     help="consecutive steps alternate between this many CUDA streams (software pipelining across steps)")
     ap.add_argument("--no-prefetch", action="store_true", help="do not run the FPS index chain on a side stream")
     ap.add_argument("--graphs", type=int, default=-1,
                     help="replay each lane's step from a CUDA graph (default: on for --impl b200; the reference launches on "
                          "the legacy default stream and cannot be captured)")
+    ap.add_argument("--room", default="8,8,3", help="synthetic room size in metres (SURVEY 8d C2: 8x8x3); a smaller room = denser cloud")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-cloud variant line (config.dense_variant)")
     ap.add_argument("--batch", type=int, default=B_SCENES)
     ap.add_argument("--points", type=int, default=N_POINTS)
     return ap.parse_args()
@@ -281,7 +283,8 @@ def main():
     lanes = [torch.cuda.Stream() for _ in range(max(a.lanes, 1))]
 
     # ---- inputs: N_ROTATE distinct batches per rank, pinned on the host and resident on the device -------------
-    base_pc, base_gt = harness.make_inputs(B, N, N_GT, seed=rank)
+    room = tuple(float(x) for x in a.room.split(","))
+    base_pc, base_gt = harness.make_inputs(B, N, N_GT, seed=rank, room=room)
     rng = np.random.default_rng(1000 + rank)
     host_pcs = []
     for i in range(N_ROTATE):
@@ -418,7 +421,11 @@ def main():
                    "host_enqueue_ms_per_step": round(enqueue_ms, 3),
                    "prefetch_fps_chain": bool(net.backbone.prefetch), "parallelism": "scene-sharded x%d, no data-path collective" % n_gpus,
                    "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (N_ROTATE, N_ROTATE * B * N * 16 / 1e6),
-                   "tf32": "torch defaults (cudnn conv TF32 allowed) for the torch-side 1x1 convs; all libb200pc kernels fp32"},
+                   "tf32": "torch defaults (cudnn conv TF32 allowed) for the torch-side 1x1 convs; all libb200pc kernels fp32",
+                   "room_m": a.room,
+                   "neighbour_lists": "fused SA kernel feeds only the 16-slot units of each ball-query list that hold distinct "
+                                      "neighbours through the MLP (the reference pads short lists with copies of the first hit; "
+                                      "max over duplicated rows is unchanged) -- gain depends on point density, see dense_variant"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / a.steps, 4)},
         "gpu_launches": int(launches),
@@ -504,7 +511,8 @@ def main():
         if a.impl == "b200":
             try:
                 nms = importlib.import_module("utils.nms")
-                from oracle import oracle as orc
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import oracle as orc  # oracle/oracle.py (the module, not the directory as a namespace package)
                 rb = np.stack([cases.aabb_boxes(i, 64, 18) for i in range(8)])
                 cen = torch.from_numpy(((rb[:, :, 0:3] + rb[:, :, 3:6]) / 2).astype(np.float32)).to(dev)
                 siz = torch.from_numpy(rb[:, :, 3:6] - rb[:, :, 0:3]).to(dev)
@@ -533,6 +541,17 @@ def main():
             line["e2e"]["h2d_bytes_per_step"] = h2d
         elif n_gpus == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(torch, N)
+        if a.impl == "b200" and n_gpus == 1 and not a.no_dense and a.room == "8,8,3":
+            try:  # same workload on a 6x denser cloud: SA1 balls hold ~55 of 64 distinct neighbours (little to compact)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "60", "--warmup", "5", "--room", "3.2,3.2,1.2",
+                                    "--no-ref", "--no-cpu-baseline", "--no-breakdown", "--no-dense", "--lanes", str(a.lanes),
+                                    "--batch", str(B), "--points", str(N)], capture_output=True, text=True, timeout=600,
+                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                line["config"]["dense_variant"] = {"room_m": "3.2,3.2,1.2", "value": d.get("value"), "e2e": d.get("e2e", {}).get("value"),
+                                                   "unit": "scenes/s", "ms_per_step": d.get("ms_per_step")}
+            except Exception as e:  # noqa: BLE001
+                line["config"]["dense_variant"] = {"error": str(e)[:200]}
         if a.impl == "b200" and n_gpus == 1 and not a.no_ref:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6",

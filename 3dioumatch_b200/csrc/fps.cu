@@ -94,8 +94,8 @@ __device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned remot
 // Per iteration:  PPT branch-free distance updates -> warp arg-max (2 x redux.sync) -> CTA arg-max through shared
 // memory -> [cluster] each CTA pushes its 32-byte record into every peer's shared memory with st.async, which also
 // signals the peer's mbarrier (complete_tx); every thread waits on its own CTA's mbarrier.  No cluster-wide barrier.
-template <int THREADS, int PPT>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int THREADS, int PPT, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
   constexpr int NWARP = THREADS / 32;
   extern __shared__ float s_xyz[];  // [PPT][THREADS][3]
@@ -339,17 +339,25 @@ int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx
 // ---- host side -----------------------------------------------------------------------------------
 typedef void (*fps_fn)(int, int, int, const float *, int32_t *);
 
-template <int THREADS>
+template <int THREADS, int MINB = 1>
 static fps_fn pick_ppt(int ppt, int *ppt_out) {
-  constexpr int MAXP = THREADS >= 512 ? 20 : 32;  // register budget: 4 registers per resident point
+  constexpr int MAXP = THREADS * MINB >= 512 ? 20 : 32;  // register budget: 4 registers per resident point
 #define B200_FPS_CASE(P)                     \
   if (P <= MAXP && ppt <= P) {               \
     *ppt_out = P;                            \
-    return fps_cluster_kernel<THREADS, (P <= MAXP ? P : 1)>; \
+    return fps_cluster_kernel<THREADS, (P <= MAXP ? P : 1), MINB>; \
   }
   B200_FPS_CASE(1) B200_FPS_CASE(2) B200_FPS_CASE(4) B200_FPS_CASE(6) B200_FPS_CASE(8) B200_FPS_CASE(10)
   B200_FPS_CASE(12) B200_FPS_CASE(16) B200_FPS_CASE(20) B200_FPS_CASE(24) B200_FPS_CASE(32)
 #undef B200_FPS_CASE
+  *ppt_out = 0;
+  return nullptr;
+}
+
+// two co-resident CTAs per SM (128 registers per thread): the latency-bound reduction/exchange half of one CTA's
+// iteration runs under the issue-bound update half of the other, so a scene costs about half the SM-time.
+static fps_fn pick_kernel2(int threads, int ppt, int *ppt_out) {
+  if (threads == 256 && ppt >= 8) return pick_ppt<256, 2>(ppt, ppt_out);
   *ppt_out = 0;
   return nullptr;
 }
@@ -418,8 +426,10 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
   // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
   // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.
-  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0;
+  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0, env_pack = 0;
   if (env_cs < 0) {
+    const char *ep = getenv("B200_FPS_PACK");  // 1: two CTAs per SM for the large-cloud shapes (pick_kernel2)
+    env_pack = ep ? atoi(ep) : 0;
     const char *e = getenv("B200_FPS_CLUSTER");
     env_cs = e ? atoi(e) : 0;
     e = getenv("B200_FPS_THREADS");
@@ -447,7 +457,8 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       if (((cs * th) % bs) != 0 && force_threads <= 0 && force_cs <= 0) continue;
       const int need = ceil_div(N, cs * th);
       int ppt = 0;
-      fps_fn fn = pick_kernel(th, need, &ppt);
+      fps_fn fn = env_pack ? pick_kernel2(th, need, &ppt) : nullptr;
+      if (!fn) fn = pick_kernel(th, need, &ppt);
       if (!fn) continue;
       const size_t smem = sizeof(float) * 3 * (size_t)ppt * th;
       if (smem > 200 * 1024) continue;

@@ -34,6 +34,7 @@ namespace b200 {
 struct PackParams {
   const float *w[TC_MAXL];
   int cin[TC_MAXL], cout[TC_MAXL], nkb[TC_MAXL], nhalf[TC_MAXL], rows[TC_MAXL];
+  int ld[TC_MAXL];  // row stride of the source matrix (== cin unless a column range of a wider matrix is packed)
   size_t off[TC_MAXL];
   int nl, perm_c;  // perm_c >= 0: layer 0 column k reads source channel (k < perm_c ? 3 + k : k - perm_c)
 };
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint
       const int k = kb * 32 + chunk * 4 + e;
       int src = k;
       if (l == 0 && p.perm_c >= 0) src = k < p.perm_c ? 3 + k : k - p.perm_c;
-      v[e] = (n < p.cout[l] && k < p.cin[l]) ? p.w[l][(size_t)n * p.cin[l] + src] : 0.f;
+      v[e] = (n < p.cout[l] && k < p.cin[l]) ? p.w[l][(size_t)n * p.ld[l] + src] : 0.f;
       tc::split_tf32(v[e], hi[e], lo[e]);
     }
     const size_t stage_bytes = (size_t)rows * 256;  // hi rows | lo rows, 128 B each
@@ -489,11 +490,87 @@ bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200
   return true;
 }
 
+// wx[k][c] = scale1[c] * W1[c][k] for the three relative-xyz input columns of layer 1 (zero without xyz channels)
+__global__ void __launch_bounds__(128) tc_wx_kernel(int cout, int ld, int use_xyz, const float *__restrict__ w,
+                                                   const float *__restrict__ scale, float *__restrict__ wx) {
+  const int c = threadIdx.x;
+  for (int k = 0; k < 3; ++k) wx[k * 128 + c] = (use_xyz && c < cout) ? scale[c] * w[(size_t)c * ld + k] : 0.f;
+}
+
+static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                             const float *xyz, const float *feat_pm, const float *new_xyz, const int32_t *idx,
+                             int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
+                             cudaStream_t stream, const int32_t *idx3, const float *w3, const float *rel3,
+                             const float *wx);
+
+static bool sa_tc_persist() {
+  static int persist = -1;
+  if (persist < 0) {
+    const char *e = getenv("B200_SA_TC_PERSIST");
+    persist = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return persist != 0;
+}
+
+// Factorised first layer (persistent kernel only).  conv1([rel xyz | f_j]) = W1x * rel + W1f * f_j and the second term
+// belongs to the SOURCE POINT j, not to the grouped row: it is computed once per point by a plain tensor-core row GEMM
+// (pass 1: B*N rows instead of B*M*nsample), and the fused kernel gathers those 4*H1-byte rows instead of the 4*C-byte
+// feature rows, adds the three xyz FMAs + ReLU in the producers and runs layers 2.. only (pass 2).  Same math up to fp32
+// summation order (the 1e-5 parity bar is checked both ways: B200_SA_TC_FACTOR=0 keeps the unfactorised path).
 int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
                  const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
                  const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream, const int32_t *idx3,
                  const float *w3, const float *rel3) {
-  TcParams p;
+  const char *fe = getenv("B200_SA_TC_FACTOR");  // read per call: the parity tests toggle it in-process
+  const int H1 = layers[0].cout;
+  const bool factor = sa_tc_persist() && !(fe && atoi(fe) == 0) && num_layers >= 3 && C >= 32 && (C & 3) == 0 && feat_pm &&
+                      ((((uintptr_t)feat_pm) & 15) == 0) && H1 <= 128 && (long long)B * N < (1ll << 30);
+  if (!factor)
+    return sa_tc_launch_core(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, feat_pm, new_xyz, idx, num_layers,
+                             layers, out, out_pm, stream, idx3, w3, rel3, nullptr);
+  // ---- pass 1: P[(b,n)][c] = scale1[c] * sum_k W1[c][xyz_cols + k] * f[b][n][k] + shift1[c] ----------------------------
+  const int rows_total = B * N;
+  const int nkb = (C + 31) / 32;
+  const size_t p_bytes = ((size_t)rows_total * H1 * sizeof(float) + 255) & ~(size_t)255;
+  const size_t wx_bytes = 3 * 128 * sizeof(float);
+  const size_t pack_bytes = (size_t)nkb * H1 * 256;
+  uint8_t *buf = nullptr;
+  B200_CUDA_OK(scratch_alloc((void **)&buf, p_bytes + wx_bytes + pack_bytes + 256, stream));
+  float *P = reinterpret_cast<float *>(buf);
+  float *wx = reinterpret_cast<float *>(buf + p_bytes);
+  uint8_t *packed = buf + p_bytes + wx_bytes;
+  int *counter = reinterpret_cast<int *>(packed + pack_bytes);
+  PackParams pk;
+  pk.nl = 1; pk.perm_c = -1;
+  pk.w[0] = layers[0].weight + (use_xyz ? 3 : 0);
+  pk.cin[0] = C; pk.ld[0] = layers[0].cin; pk.cout[0] = H1; pk.nkb[0] = nkb; pk.nhalf[0] = 1; pk.rows[0] = H1; pk.off[0] = 0;
+  tc_pack_weights_kernel<<<dim3(32, 1), 256, 0, stream>>>(pk, packed);
+  B200_LAUNCH_OK("tc_pack_weights_kernel");
+  tc_wx_kernel<<<1, 128, 0, stream>>>(H1, layers[0].cin, use_xyz ? 1 : 0, layers[0].weight, layers[0].scale, wx);
+  B200_LAUNCH_OK("tc_wx_kernel");
+  TcParams g = {};
+  g.mode = 2; g.rowout = 1; g.rows_total = rows_total;
+  g.B = 1; g.N = rows_total; g.M = rows_total; g.C = C; g.ns = 32; g.G = TC_ROWS / 32; g.use_xyz = 0; g.nl = 1;
+  g.inv_r = 1.0f; g.feat_pm = feat_pm; g.out_pm = P; g.packed = packed; g.vec_gather = 1;
+  g.wslot_bytes = H1 * 128; g.small_off = 128;
+  g.L[0].scale = layers[0].scale; g.L[0].shift = layers[0].shift; g.L[0].cin = C; g.L[0].cout = H1; g.L[0].nkb = nkb;
+  g.L[0].nhalf = 1; g.L[0].rows = H1; g.L[0].packed_off = 0;
+  int rc = sa_tcp_launch(g, counter, nullptr, stream);
+  if (rc == 0)  // ---- pass 2: gather rows of P, + wx * rel, ReLU, layers 2.. -----------------------------------------
+    rc = sa_tc_launch_core(B, N, M, H1, radius, nsample, use_xyz, normalize_xyz, xyz, P, new_xyz, idx, num_layers - 1,
+                           layers + 1, out, out_pm, stream, idx3, w3, rel3, wx);
+  cudaFreeAsync(buf, stream);
+  return rc;
+}
+
+static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                             const float *xyz, const float *feat_pm, const float *new_xyz, const int32_t *idx,
+                             int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
+                             cudaStream_t stream, const int32_t *idx3, const float *w3, const float *rel3,
+                             const float *wx) {
+  TcParams p = {};
+  p.pre = wx ? 1 : 0;
+  p.wx = wx;
   p.mode = idx3 ? 1 : 0;
   p.idx3 = idx3; p.w3 = w3; p.rel3 = rel3;
   PackParams pk;
@@ -516,11 +593,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     for (int l = 0; l + 1 < num_layers; ++l) mx = layers[l].cout > mx ? layers[l].cout : mx;
     return mx * 128;  // one slot holds W_hi or W_lo of a k-block
   };
-  static int persist = -1;
-  if (persist < 0) {
-    const char *e = getenv("B200_SA_TC_PERSIST");
-    persist = (e && atoi(e) == 0) ? 0 : 1;
-  }
+  const bool persist = sa_tc_persist();
   const bool can_compact = cout_last == 128 && hid_max <= 128;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float);
   const size_t smem_compact = fixed + (size_t)r1 + 4 * (size_t)slot_for(64);
@@ -540,7 +613,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
                               : fixed + (size_t)r1 + 4 * (size_t)p.wslot_bytes + 128 * 36 * sizeof(float);
   size_t off = 0;
   pk.nl = num_layers;
-  pk.perm_c = use_xyz ? C : -1;
+  pk.perm_c = (use_xyz && !p.pre) ? C : -1;
   for (int l = 0; l < num_layers; ++l) {
     TcLayer &t = p.L[l];
     const bool last = l == num_layers - 1;
@@ -549,7 +622,7 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
     t.rows = last ? last_rows : layers[l].cout;
     t.nhalf = layers[l].cout / t.rows;
     t.packed_off = off;
-    pk.w[l] = layers[l].weight; pk.cin[l] = t.cin; pk.cout[l] = t.cout; pk.nkb[l] = t.nkb; pk.nhalf[l] = t.nhalf;
+    pk.w[l] = layers[l].weight; pk.cin[l] = t.cin; pk.ld[l] = t.cin; pk.cout[l] = t.cout; pk.nkb[l] = t.nkb; pk.nhalf[l] = t.nhalf;
     pk.rows[l] = t.rows;
     pk.off[l] = off;
     off += (size_t)t.nhalf * t.nkb * (size_t)t.rows * 256;

@@ -49,6 +49,13 @@ struct TcParams {
   const int32_t *idx3;   // (B, M*ns, 3)
   const float *w3;       // (B, M*ns, 3)
   const float *rel3;     // (B, M*ns, 3) or NULL
+  // factorised first layer (sa_tcp.cu): W1 * [rel xyz | f] = W1x * rel + W1f * f, and W1f * f depends on the source point
+  // only.  Pass 1 (mode 2, rowout): plain row GEMM P = scale1 * (W1f * f) + shift1 over all B*N points, rows written
+  // point-major without ReLU.  Pass 2 (pre = 1): the producers gather rows of P (or blend three of them in mode 1),
+  // add wx[k][c] * rel[k] (wx = scale1 * W1x, [3][128]) and apply the ReLU on their way into the operand ring; the
+  // kernel then runs layers 2.. only.
+  int pre, rowout, rows_total;
+  const float *wx;
   TcLayer L[TC_MAXL];
 };
 

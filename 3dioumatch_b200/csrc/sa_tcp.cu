@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   float *s_scale = reinterpret_cast<float *>(R2 + p.nslots * p.wslot_bytes);  // [TC_MAXL][256]
   float *s_shift = s_scale + TC_MAXL * 256;
   float *s_partial = s_shift + TC_MAXL * 256;                                // [2][4][256] per-warp maxima (nsample > 32)
+  float *s_wx = s_partial + 2 * 4 * 256;                                     // [3][128] scale1 * W1x (factorised layer 1)
 
   __shared__ uint64_t full_a[TP_ASTAGES], empty_a[TP_ASTAGES], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
   __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free, tq_full[TP_TQ], tq_empty[TP_TQ];
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     s_scale[e] = c < p.L[l].cout ? p.L[l].scale[c] : 0.f;
     s_shift[e] = c < p.L[l].cout ? p.L[l].shift[c] : 0.f;
   }
+  for (int e = tid; e < 3 * 128; e += TP_THREADS) s_wx[e] = p.pre ? p.wx[e] : 0.f;
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -429,7 +431,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       if (t < 0) break;
       int b, m0, g_here, slot, gi;
       bool valid;
-      if (p.units) {
+      if (p.mode == 2) {
+        // plain row GEMM (pass 1 of the factorised layer 1): tile row = point t * 128 + row of the flattened (B*N, C) input
+        b = 0; m0 = 0; g_here = 1; gi = 0; slot = 0;
+        valid = t * TC_ROWS + row < p.rows_total;
+      } else if (p.units) {
         // compacted tile: 8 units of 16 slots, each from the centre the unit list names
         const int u = t * 8 + (row >> 4);
         valid = u < __ldg(p.total_units);
@@ -456,6 +462,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
       }
       const float *frow = (valid && C > 0 && p.mode == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
+      if (valid && p.mode == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * C;
       float rel[3] = {0.f, 0.f, 0.f};
       const float *f3[3] = {nullptr, nullptr, nullptr};
       float wt[3] = {0.f, 0.f, 0.f};
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].y = __fmaf_rn(a2.y, wt[2], __fmaf_rn(a0.y, wt[0], __fmul_rn(a1.y, wt[1])));
             v[c].z = __fmaf_rn(a2.z, wt[2], __fmaf_rn(a0.z, wt[0], __fmul_rn(a1.z, wt[1])));
             v[c].w = __fmaf_rn(a2.w, wt[2], __fmaf_rn(a0.w, wt[0], __fmul_rn(a1.w, wt[1])));
-          } else if (valid && p.mode == 0 && p.vec_gather && ch + 3 < C) {
+          } else if (valid && p.mode != 1 && p.vec_gather && ch + 3 < C) {
             v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
           } else {
             float e4[4];
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               float x = 0.f;
               if (valid) {
                 if (k < C) {
-                  x = p.mode == 0 ? frow[k]
+                  x = p.mode != 1 ? frow[k]
                                   : __fmaf_rn(f3[2][k], wt[2], __fmaf_rn(f3[0][k], wt[0], __fmul_rn(f3[1][k], wt[1])));
                 } else if (p.use_xyz && k < C + 3) {
                   x = rel[k - C];
@@ -509,6 +516,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               e4[e] = x;
             }
             v[c] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+          }
+          if (p.pre) {
+            // factorised layer 1: v holds scale1 * (W1f * f) + shift1 of the source point (or the blend of three);
+            // add the relative-xyz part of the layer and apply its ReLU (rel = 0 and v = 0 for rows past the end)
+            const float4 w0 = *reinterpret_cast<const float4 *>(s_wx + ch);
+            const float4 w1 = *reinterpret_cast<const float4 *>(s_wx + 128 + ch);
+            const float4 w2 = *reinterpret_cast<const float4 *>(s_wx + 256 + ch);
+            v[c].x = fmaxf(__fmaf_rn(w2.x, rel[2], __fmaf_rn(w1.x, rel[1], __fmaf_rn(w0.x, rel[0], v[c].x))), 0.f);
+            v[c].y = fmaxf(__fmaf_rn(w2.y, rel[2], __fmaf_rn(w1.y, rel[1], __fmaf_rn(w0.y, rel[0], v[c].y))), 0.f);
+            v[c].z = fmaxf(__fmaf_rn(w2.z, rel[2], __fmaf_rn(w1.z, rel[1], __fmaf_rn(w0.z, rel[0], v[c].z))), 0.f);
+            v[c].w = fmaxf(__fmaf_rn(w2.w, rel[2], __fmaf_rn(w1.w, rel[1], __fmaf_rn(w0.w, rel[0], v[c].w))), 0.f);
           }
         }
       };
@@ -638,6 +656,26 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 v[c * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
                 v[c * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
               }
+              if (p.rowout) {
+                // plain row GEMM: affine without the ReLU, this row's 32 columns stored as one 128-byte run
+                const size_t grow = (size_t)t * TC_ROWS + row;
+                if (grow < (size_t)p.rows_total) {
+                  float4 *dst = reinterpret_cast<float4 *>(p.out_pm + grow * cout + c0);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
+                    const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
+                    float4 o;
+                    o.x = fmaf(__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]), s4.x, h4.x);
+                    o.y = fmaf(__uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]), s4.y, h4.y);
+                    o.z = fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z);
+                    o.w = fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w);
+                    dst[c] = o;
+                  }
+                }
+                TP_LAP(18);
+                continue;
+              }
               if (p.units) {
                 // 16-row units: lanes 0-15 / 16-31 reduce separately; a centre's units meet in global memory through an
                 // integer atomicMax (outputs are >= 0 after the ReLU, so the int order is the float order; the
@@ -686,7 +724,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               TP_LAP(18);
             }
           }
-          if (ns > 32 && !p.units) {
+          if (ns > 32 && !p.units && !p.rowout) {
             TP_BEGIN();
             // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -767,10 +805,10 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
     if (p.out_pm) B200_CUDA_OK(cudaMemsetAsync(p.out_pm, 0, (size_t)p.B * cout * p.M * sizeof(float), stream));
   }
   p.tiles_per_scene = ceil_div(p.M, p.G);
-  p.total_tiles = p.B * p.tiles_per_scene;
+  p.total_tiles = p.mode == 2 ? ceil_div(p.rows_total, TC_ROWS) : p.B * p.tiles_per_scene;
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
-  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float);
+  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float);
   static int force_astages = -1;
   if (force_astages < 0) {
     const char *e = getenv("B200_SA_TC_ASTAGES");

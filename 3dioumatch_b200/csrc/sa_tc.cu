@@ -36,12 +36,28 @@ struct PackParams {
   int cin[TC_MAXL], cout[TC_MAXL], nkb[TC_MAXL], nhalf[TC_MAXL], rows[TC_MAXL];
   int ld[TC_MAXL];  // row stride of the source matrix (== cin unless a column range of a wider matrix is packed)
   size_t off[TC_MAXL];
+  // grid row nl: zero the two tile counters of the persistent kernel and, for a factorised first layer, build
+  // wx[k][c] = scale1[c] * W1[c][k] for its three relative-xyz input columns (zero without xyz channels)
+  int *counters;
+  float *wx;
+  const float *wx_w, *wx_scale;
+  int wx_ld, wx_cout, wx_xyz;
   int nl, perm_c;  // perm_c >= 0: layer 0 column k reads source channel (k < perm_c ? 3 + k : k - perm_c)
 };
 
 __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint8_t *__restrict__ packed) {
   const int l = blockIdx.y;
-  if (l >= p.nl) return;
+  if (l >= p.nl) {
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < 2 && p.counters) p.counters[threadIdx.x] = 0;
+      if (p.wx_w && threadIdx.x < 128) {
+        const int c = threadIdx.x;
+        for (int k = 0; k < 3; ++k)
+          p.wx[k * 128 + c] = (k < p.wx_xyz && c < p.wx_cout) ? p.wx_scale[c] * p.wx_w[(size_t)c * p.wx_ld + k] : 0.f;
+      }
+    }
+    return;
+  }
   const int rows = p.rows[l];
   const int items = p.nhalf[l] * p.nkb[l] * rows * 8;  // (half, kb, row, chunk)
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
@@ -490,19 +506,6 @@ bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200
   return true;
 }
 
-// wx[k][c] = scale1[c] * W1[c][k] for the three relative-xyz input columns of layer 1 (zero without xyz channels)
-__global__ void __launch_bounds__(128) tc_wx_kernel(int cout, int ld, int use_xyz, const float *__restrict__ w,
-                                                   const float *__restrict__ scale, float *__restrict__ wx) {
-  const int c = threadIdx.x;
-  for (int k = 0; k < 3; ++k) wx[k * 128 + c] = (use_xyz && c < cout) ? scale[c] * w[(size_t)c * ld + k] : 0.f;
-}
-
-static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
-                             const float *xyz, const float *feat_pm, const float *new_xyz, const int32_t *idx,
-                             int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
-                             cudaStream_t stream, const int32_t *idx3, const float *w3, const float *rel3,
-                             const float *wx);
-
 static bool sa_tc_persist() {
   static int persist = -1;
   if (persist < 0) {
@@ -517,6 +520,18 @@ static bool sa_tc_persist() {
 // (pass 1: B*N rows instead of B*M*nsample), and the fused kernel gathers those 4*H1-byte rows instead of the 4*C-byte
 // feature rows, adds the three xyz FMAs + ReLU in the producers and runs layers 2.. only (pass 2).  Same math up to fp32
 // summation order (the 1e-5 parity bar is checked both ways: B200_SA_TC_FACTOR=0 keeps the unfactorised path).
+struct FactorPlan {
+  const b200_mlp_layer *l1;  // the original first layer: weight (H1, cin0), cin0 = (use_xyz ? 3 : 0) + C_feat
+  const float *feat_pm;      // (B*N, C_feat) point-major input features
+  int C_feat, rows_total;
+};
+
+static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                             const float *xyz, const float *feat_pm, const float *new_xyz, const int32_t *idx,
+                             int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
+                             cudaStream_t stream, const int32_t *idx3, const float *w3, const float *rel3,
+                             const FactorPlan *plan);
+
 int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
                  const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
                  const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream, const int32_t *idx3,
@@ -528,57 +543,28 @@ int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_
   if (!factor)
     return sa_tc_launch_core(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, feat_pm, new_xyz, idx, num_layers,
                              layers, out, out_pm, stream, idx3, w3, rel3, nullptr);
-  // ---- pass 1: P[(b,n)][c] = scale1[c] * sum_k W1[c][xyz_cols + k] * f[b][n][k] + shift1[c] ----------------------------
-  const int rows_total = B * N;
-  const int nkb = (C + 31) / 32;
-  const size_t p_bytes = ((size_t)rows_total * H1 * sizeof(float) + 255) & ~(size_t)255;
-  const size_t wx_bytes = 3 * 128 * sizeof(float);
-  const size_t pack_bytes = (size_t)nkb * H1 * 256;
-  uint8_t *buf = nullptr;
-  B200_CUDA_OK(scratch_alloc((void **)&buf, p_bytes + wx_bytes + pack_bytes + 256, stream));
-  float *P = reinterpret_cast<float *>(buf);
-  float *wx = reinterpret_cast<float *>(buf + p_bytes);
-  uint8_t *packed = buf + p_bytes + wx_bytes;
-  int *counter = reinterpret_cast<int *>(packed + pack_bytes);
-  PackParams pk;
-  pk.nl = 1; pk.perm_c = -1;
-  pk.w[0] = layers[0].weight + (use_xyz ? 3 : 0);
-  pk.cin[0] = C; pk.ld[0] = layers[0].cin; pk.cout[0] = H1; pk.nkb[0] = nkb; pk.nhalf[0] = 1; pk.rows[0] = H1; pk.off[0] = 0;
-  tc_pack_weights_kernel<<<dim3(32, 1), 256, 0, stream>>>(pk, packed);
-  B200_LAUNCH_OK("tc_pack_weights_kernel");
-  tc_wx_kernel<<<1, 128, 0, stream>>>(H1, layers[0].cin, use_xyz ? 1 : 0, layers[0].weight, layers[0].scale, wx);
-  B200_LAUNCH_OK("tc_wx_kernel");
-  TcParams g = {};
-  g.mode = 2; g.rowout = 1; g.rows_total = rows_total;
-  g.B = 1; g.N = rows_total; g.M = rows_total; g.C = C; g.ns = 32; g.G = TC_ROWS / 32; g.use_xyz = 0; g.nl = 1;
-  g.inv_r = 1.0f; g.feat_pm = feat_pm; g.out_pm = P; g.packed = packed; g.vec_gather = 1;
-  g.wslot_bytes = H1 * 128; g.small_off = 128;
-  g.L[0].scale = layers[0].scale; g.L[0].shift = layers[0].shift; g.L[0].cin = C; g.L[0].cout = H1; g.L[0].nkb = nkb;
-  g.L[0].nhalf = 1; g.L[0].rows = H1; g.L[0].packed_off = 0;
-  int rc = sa_tcp_launch(g, counter, nullptr, stream);
-  if (rc == 0)  // ---- pass 2: gather rows of P, + wx * rel, ReLU, layers 2.. -----------------------------------------
-    rc = sa_tc_launch_core(B, N, M, H1, radius, nsample, use_xyz, normalize_xyz, xyz, P, new_xyz, idx, num_layers - 1,
-                           layers + 1, out, out_pm, stream, idx3, w3, rel3, wx);
-  cudaFreeAsync(buf, stream);
-  return rc;
+  FactorPlan plan;
+  plan.l1 = &layers[0]; plan.feat_pm = feat_pm; plan.C_feat = C; plan.rows_total = B * N;
+  // the fused kernel sees H1 "feature" channels (rows of P) and the layers after the first
+  return sa_tc_launch_core(B, N, M, H1, radius, nsample, use_xyz, normalize_xyz, xyz, nullptr, new_xyz, idx, num_layers - 1,
+                           layers + 1, out, out_pm, stream, idx3, w3, rel3, &plan);
 }
 
 static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
                              const float *xyz, const float *feat_pm, const float *new_xyz, const int32_t *idx,
                              int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
                              cudaStream_t stream, const int32_t *idx3, const float *w3, const float *rel3,
-                             const float *wx) {
+                             const FactorPlan *plan) {
   TcParams p = {};
-  p.pre = wx ? 1 : 0;
-  p.wx = wx;
+  p.pre = plan ? 1 : 0;
   p.mode = idx3 ? 1 : 0;
   p.idx3 = idx3; p.w3 = w3; p.rel3 = rel3;
-  PackParams pk;
+  PackParams pk = {};
   p.B = B; p.N = N; p.M = M; p.C = C; p.ns = nsample; p.G = TC_ROWS / nsample; p.use_xyz = use_xyz ? 1 : 0;
   p.nl = num_layers;
   p.inv_r = normalize_xyz ? (float)(1.0 / (double)radius) : 1.0f;
   p.xyz = xyz; p.feat_pm = feat_pm; p.new_xyz = new_xyz; p.idx = idx; p.out = out; p.out_pm = out_pm;
-  p.vec_gather = (C > 0 && (C & 3) == 0 && ((((uintptr_t)feat_pm) & 15) == 0)) ? 1 : 0;
+  p.vec_gather = plan ? 1 : ((C > 0 && (C & 3) == 0 && ((((uintptr_t)feat_pm) & 15) == 0)) ? 1 : 0);
   // ---- geometry: rows per weight stage, shared-memory regions, TMEM columns ---------------------------------------
   const int cout_last = layers[num_layers - 1].cout;
   int hid_max = 0;
@@ -613,7 +599,7 @@ static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsamp
                               : fixed + (size_t)r1 + 4 * (size_t)p.wslot_bytes + 128 * 36 * sizeof(float);
   size_t off = 0;
   pk.nl = num_layers;
-  pk.perm_c = (use_xyz && !p.pre) ? C : -1;
+  pk.perm_c = (use_xyz && !plan) ? C : -1;
   for (int l = 0; l < num_layers; ++l) {
     TcLayer &t = p.L[l];
     const bool last = l == num_layers - 1;
@@ -627,18 +613,49 @@ static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsamp
     pk.off[l] = off;
     off += (size_t)t.nhalf * t.nkb * (size_t)t.rows * 256;
   }
+  // factorised first layer: its feature columns are one more entry of the same packing launch (num_layers <= TC_MAXL - 1)
+  TcParams g = {};
+  size_t p_bytes = 0;
+  if (plan) {
+    const int l = num_layers, H1 = plan->l1->cout, Cf = plan->C_feat, cin0 = plan->l1->cin;
+    pk.nl = num_layers + 1;
+    pk.w[l] = plan->l1->weight + (cin0 - Cf);  // skip the xyz columns
+    pk.cin[l] = Cf; pk.ld[l] = cin0; pk.cout[l] = H1; pk.nkb[l] = (Cf + 31) / 32; pk.nhalf[l] = 1; pk.rows[l] = H1;
+    pk.off[l] = off;
+    pk.wx_w = plan->l1->weight; pk.wx_scale = plan->l1->scale; pk.wx_ld = cin0; pk.wx_cout = H1; pk.wx_xyz = cin0 - Cf;
+    g.mode = 2; g.rowout = 1; g.rows_total = plan->rows_total;
+    g.B = 1; g.N = plan->rows_total; g.M = plan->rows_total; g.C = Cf; g.ns = 32; g.G = TC_ROWS / 32; g.nl = 1;
+    g.inv_r = 1.0f; g.feat_pm = plan->feat_pm; g.vec_gather = 1;
+    g.wslot_bytes = H1 * 128; g.small_off = 128;
+    g.L[0].scale = plan->l1->scale; g.L[0].shift = plan->l1->shift; g.L[0].cin = Cf; g.L[0].cout = H1;
+    g.L[0].nkb = pk.nkb[l]; g.L[0].nhalf = 1; g.L[0].rows = H1; g.L[0].packed_off = off;
+    off += (size_t)pk.nkb[l] * H1 * 256;
+    p_bytes = ((size_t)plan->rows_total * H1 * sizeof(float) + 255) & ~(size_t)255;
+  }
+  // scratch: [packed weights | tile counters + wx (2 KB) | unit scratch | P]
   uint8_t *packed = nullptr;
   const size_t counter_off = (off + 255) & ~(size_t)255;
-  const size_t unit_bytes = (persist && !idx3) ? sa_tcp_unit_scratch_bytes(B, M, nsample) : 0;
-  B200_CUDA_OK(scratch_alloc((void **)&packed, counter_off + 256 + unit_bytes, stream));
-  tc_pack_weights_kernel<<<dim3(32, num_layers), 256, 0, stream>>>(pk, packed);
+  const size_t unit_bytes = (persist && !idx3) ? ((sa_tcp_unit_scratch_bytes(B, M, nsample) + 255) & ~(size_t)255) : 0;
+  B200_CUDA_OK(scratch_alloc((void **)&packed, counter_off + 2048 + unit_bytes + p_bytes, stream));
+  int *counters = reinterpret_cast<int *>(packed + counter_off);          // [0]: pass 2 / only pass, [1]: pass 1
+  float *wx = reinterpret_cast<float *>(packed + counter_off + 512);      // [3][128]
+  pk.counters = counters;
+  pk.wx = wx;
+  tc_pack_weights_kernel<<<dim3(32, pk.nl + 1), 256, 0, stream>>>(pk, packed);  // last row: counters (+ wx)
   B200_LAUNCH_OK("tc_pack_weights_kernel");
   p.packed = packed;
   p.nslots = 4; p.total_tiles = 0; p.tiles_per_scene = 0; p.tile_counter = nullptr; p.final_shfl = 0;
   if (persist) {
     // persistent warp-specialised kernel (sa_tcp.cu): one CTA per SM, tiles from an atomic queue
-    const int rc = sa_tcp_launch(p, reinterpret_cast<int *>(packed + counter_off),
-                                 unit_bytes ? reinterpret_cast<int *>(packed + counter_off + 256) : nullptr, stream);
+    if (plan) {
+      float *P = reinterpret_cast<float *>(packed + counter_off + 2048 + unit_bytes);
+      g.packed = packed; g.out_pm = P;
+      const int rc1 = sa_tcp_launch(g, counters + 1, nullptr, stream);  // pass 1: P = scale1 * (W1f * f) + shift1
+      if (rc1 != 0) return rc1;
+      p.feat_pm = P; p.wx = wx;
+    }
+    const int rc = sa_tcp_launch(p, counters, unit_bytes ? reinterpret_cast<int *>(packed + counter_off + 2048) : nullptr,
+                                 stream);
     if (rc != 0) return rc;
     B200_CUDA_OK(cudaFreeAsync(packed, stream));
     return 0;

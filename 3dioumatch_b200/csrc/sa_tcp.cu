@@ -828,7 +828,7 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
     B200_CUDA_OK(cudaFuncSetAttribute(sa_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  B200_CUDA_OK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), stream));
+  // the tile counter was zeroed in stream order by tc_pack_weights_kernel (sa_tc.cu)
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   sa_tcp_kernel<<<grid, TP_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_tcp_kernel");

@@ -29,7 +29,7 @@ N_ROTATE = 32  # distinct input batches cycled through the timed region: 32 x 5.
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,7 +57,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.stop_flag = gpu_index, False
+        self.gpu, self.stop_flag, self.armed = gpu_index, False, False
         self.sm, self.max_sm, self.reasons, self.power = [], None, set(), []
         self.nvml = None
         try:
@@ -109,6 +109,8 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
 
     def run(self):
+        # started before the warm-up (NVML's first queries take a driver lock for tens of milliseconds, which showed up as
+        # a stalled launch thread at the start of the timed region); samples are kept from arm() on
         while not self.stop_flag:
             try:
                 if self.nvml:
@@ -117,7 +119,12 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.02 if self.nvml else 0.2)
+            if not self.armed:
+                self.sm, self.power, self.reasons = [], [], set()
+            time.sleep(0.05 if self.nvml else 0.2)
+
+    def arm(self):
+        self.armed = True
 
     def summary(self):
         sm = sorted(self.sm)
@@ -388,12 +395,17 @@ def main():
             net(dev_pcs[0], dev_gt)          # one eager step: how many libb200pc kernels a step launches
             torch.cuda.synchronize()
             launches_per_step = cabi.launch_count() - c0
+    import gc
     with torch.no_grad():
+        sampler = ClockSampler(local)
+        sampler.start()
         for i in range(max(a.warmup, 3)):
             step_resident(i)
             step_e2e(i)
-        sampler = ClockSampler(local)
-        sampler.start()
+        torch.cuda.synchronize()
+        gc.collect()
+        gc.disable()          # no collector pause inside the timed regions
+        sampler.arm()
         launches0 = cabi.launch_count() if cabi else 0
         ms_res = timed(step_resident, a.steps)
         enqueue_ms = timed.enqueue_ms
@@ -401,8 +413,10 @@ def main():
         if use_graphs:
             launches = launches_per_step * a.steps   # replayed from the captured graphs (not re-counted by the library)
         ms_e2e = timed(step_e2e, a.steps)
+        enqueue_e2e_ms = timed.enqueue_ms
         sampler.stop_flag = True
         sampler.join(timeout=2)
+        gc.enable()
 
     scenes = world * B * a.steps if distributed else B * a.steps
     n_gpus = world if distributed else 1
@@ -425,9 +439,11 @@ def main():
                    "room_m": a.room,
                    "neighbour_lists": "fused SA kernel feeds only the 16-slot units of each ball-query list that hold distinct "
                                       "neighbours through the MLP (the reference pads short lists with copies of the first hit; "
-                                      "max over duplicated rows is unchanged) -- gain depends on point density, see dense_variant"},
+                                      "max over duplicated rows is unchanged) -- gain depends on point density, see dense_variant",
+                   "first_layer": "SA layers with >= 32 feature channels run layer 1 factorised: W1f*f once per source point "
+                                  "(tensor-core row GEMM), xyz FMAs + ReLU in the gather (B200_SA_TC_FACTOR=0 disables)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / a.steps, 4)},
+                "ms_per_step": round(ms_e2e / a.steps, 4), "host_enqueue_ms_per_step": round(enqueue_e2e_ms, 4)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "b200_abi_version": (c_int, []),
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_launch_count": (ctypes.c_ulonglong, []),
+    "b200pn2_fps_set_policy": (c_int, [c_int]),
     "b200pn2_furthest_point_sampling": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -77,3 +78,11 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().b200_launch_count())
+
+
+def set_fps_policy(policy):
+    """'latency' (default; shortest serial chain) or 'throughput' (least SM-time; pipelined steps).  Returns the previous
+    policy name.  Results are bit-identical either way (include/b200_pointnet2.h: b200pn2_fps_set_policy)."""
+    names = ("latency", "throughput")
+    prev = lib().b200pn2_fps_set_policy(names.index(policy))
+    return names[prev]

@@ -87,4 +87,27 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
   return sq3(__fsub_rn(ax, bx), __fsub_rn(ay, by), __fsub_rn(az, bz));
 }
 
+// ---- packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2: one issue slot per two IEEE-rounded fp32 operations) ---------
+// Same rounding per element as the scalar intrinsics above, so the squared-distance sequence stays bit-exact.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// (a - b)^2 summed over x, y, z for two points at once: fma(dz,dz, fma(dx,dx, dy*dy)) per element
+__device__ __forceinline__ f32x2 sqdist3_x2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by, f32x2 bz) {
+  f32x2 dx, dy, dz, t;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(ax), "l"(bx));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(ay), "l"(by));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(az), "l"(bz));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  return t;
+}
+
 }  // namespace b200

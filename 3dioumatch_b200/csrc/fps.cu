@@ -178,12 +178,22 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
     // dependent chain).  The left (lower-slot) entry survives ties, i.e. "first strict maximum in slot order".
     float tv[PPT];
     int ts[PPT];
+    const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-      const float d = sqdist3(px[p], py[p], pz[p], cx, cy, cz);  // :108-109 (x2 - x1)
-      const float d2 = fminf(d, pt[p]);                           // :111
-      pt[p] = d2;
-      tv[p] = d2;
+    for (int p = 0; p + 1 < PPT; p += 2) {
+      // two points per FADD2 / FMUL2 / FFMA2 (same per-element rounding as sqdist3): the update is issue-bound
+      float d0, d1;
+      unpack2(sqdist3_x2(pack2(px[p], px[p + 1]), pack2(py[p], py[p + 1]), pack2(pz[p], pz[p + 1]), cx2, cy2, cz2), d0, d1);
+      pt[p] = fminf(d0, pt[p]);              // :108-111 (x2 - x1), min with the running distance
+      pt[p + 1] = fminf(d1, pt[p + 1]);
+      tv[p] = pt[p]; tv[p + 1] = pt[p + 1];
+      ts[p] = p; ts[p + 1] = p + 1;
+    }
+    if (PPT & 1) {
+      constexpr int p = PPT - 1;
+      const float d = sqdist3(px[p], py[p], pz[p], cx, cy, cz);
+      pt[p] = fminf(d, pt[p]);
+      tv[p] = pt[p];
       ts[p] = p;
     }
 #pragma unroll
@@ -409,6 +419,22 @@ extern "C" int b200_debug_fps_profile(unsigned long long *out8) {
 }
 #endif
 
+static std::atomic<int> g_fps_policy{-1};  // -1: not initialised (B200_FPS_POLICY, default 0 = latency)
+static int fps_policy() {
+  int v = g_fps_policy.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("B200_FPS_POLICY");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+    g_fps_policy.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+extern "C" int b200pn2_fps_set_policy(int policy) {
+  const int prev = fps_policy();
+  g_fps_policy.store(policy == 1 ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
 extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx, float *scratch,
                                                b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -440,6 +466,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   }
   const int force_cs = N >= env_min_n ? env_cs : 0, force_threads = N >= env_min_n ? env_threads : 0;
   const int sms = num_sms();
+  const bool throughput = fps_policy() == 1;
   int best_cs = 0, best_ppt = 0, threads = 0;
   fps_fn best_fn = nullptr;
   double best_cost = 1e300;
@@ -479,7 +506,8 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       const bool ties = ((cs * th) % bs) != 0;
       const double iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
                           (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 260.0 : 0.0);  // >8: non-portable size; also keeps half the SMs free for the feature kernels
-      const double cost = waves * iter;
+      // latency policy: serial chain length; throughput policy: SM-cycles per scene (cs CTAs hold an SM each)
+      const double cost = throughput ? waves * iter * cs : waves * iter;
       if (cost < best_cost) {
         best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th;
       }

@@ -69,11 +69,16 @@ group_points_grad_kernel(int C, int N, int MK, const float *__restrict__ grad_ou
 // compares the fp32 distance with strict `<`; fp32 bests initialised to +inf select exactly the same entries
 // (an fp32 distance is never >= 1e40 unless it is +inf/NaN, which never pass `<` in either form) and
 // (float)1e40 == +inf is what the reference stores for unfilled slots.
-constexpr int NN_TILE = 1024;
+// The tile is stored as groups of four known points, structure-of-arrays ([x0..x3][y0..y3][z0..z3], 48 B), so one
+// group is three 16-byte broadcast loads and its four squared distances are two packed-pair sequences (FADD2 / FMUL2 /
+// FFMA2: half the issue slots of the scalar form, the same IEEE rounding per element).  A group only enters the
+// reference's insertion cascade (in index order) when its smallest distance beats the current third best -- rare after
+// the first few groups.  The tail group is padded with +inf coordinates: its distances are +inf / NaN and never pass `<`.
+constexpr int NN_TILE = 2048;
 __global__ void __launch_bounds__(PO_THREADS)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
                 float *__restrict__ dist2, int32_t *__restrict__ idx) {
-  __shared__ float s_known[NN_TILE * 3];
+  __shared__ float4 s_known[NN_TILE / 4 * 3];
   const int b = blockIdx.y;
   const int j = blockIdx.x * PO_THREADS + threadIdx.x;
   const bool active = j < n;
@@ -82,29 +87,49 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     const float *u = unknown + ((size_t)b * n + j) * 3;
     ux = u[0]; uy = u[1]; uz = u[2];
   }
+  const f32x2 ux2 = pack2(ux, ux), uy2 = pack2(uy, uy), uz2 = pack2(uz, uz);
   const float inf = __int_as_float(0x7f800000);
   float best1 = inf, best2 = inf, best3 = inf;
   int besti1 = 0, besti2 = 0, besti3 = 0;
   const float *kn = known + (size_t)b * m * 3;
+  float *sk = reinterpret_cast<float *>(s_known);
   for (int t0 = 0; t0 < m; t0 += NN_TILE) {
     const int tn = min(NN_TILE, m - t0);
+    const int ng = (tn + 3) >> 2;
     __syncthreads();
-    for (int i = threadIdx.x; i < tn * 3; i += PO_THREADS) s_known[i] = kn[(size_t)t0 * 3 + i];
+    for (int i = threadIdx.x; i < ng * 4; i += PO_THREADS) {
+      const float *q = kn + (size_t)(t0 + i) * 3;
+      const bool in = i < tn;
+      float *g = sk + (i >> 2) * 12 + (i & 3);
+      g[0] = in ? q[0] : inf;
+      g[4] = in ? q[1] : inf;
+      g[8] = in ? q[2] : inf;
+    }
     __syncthreads();
     if (active) {
-#pragma unroll 4
-      for (int k = 0; k < tn; ++k) {
-        const float d = sqdist3(ux, uy, uz, s_known[k * 3], s_known[k * 3 + 1], s_known[k * 3 + 2]);  // :38 (u - x)
-        if (d < best3) {  // cheap reject; the cascade below is the reference's (:39-54)
-          if (d < best1) {
-            best3 = best2; besti3 = besti2;
-            best2 = best1; besti2 = besti1;
-            best1 = d; besti1 = t0 + k;
-          } else if (d < best2) {
-            best3 = best2; besti3 = besti2;
-            best2 = d; besti2 = t0 + k;
-          } else {
-            best3 = d; besti3 = t0 + k;
+#pragma unroll 2
+      for (int g = 0; g < ng; ++g) {
+        const float4 X = s_known[g * 3], Y = s_known[g * 3 + 1], Z = s_known[g * 3 + 2];
+        float d[4];
+        // interpolate_gpu.cu:38 (u - x)
+        unpack2(sqdist3_x2(ux2, uy2, uz2, pack2(X.x, X.y), pack2(Y.x, Y.y), pack2(Z.x, Z.y)), d[0], d[1]);
+        unpack2(sqdist3_x2(ux2, uy2, uz2, pack2(X.z, X.w), pack2(Y.z, Y.w), pack2(Z.z, Z.w)), d[2], d[3]);
+        if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < best3) {  // cheap reject (NaN never passes, as in the cascade)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = t0 + g * 4 + e;
+            if (d[e] < best3) {  // the reference's cascade (:39-54)
+              if (d[e] < best1) {
+                best3 = best2; besti3 = besti2;
+                best2 = best1; besti2 = besti1;
+                best1 = d[e]; besti1 = k;
+              } else if (d[e] < best2) {
+                best3 = best2; besti3 = besti2;
+                best2 = d[e]; besti2 = k;
+              } else {
+                best3 = d[e]; besti3 = k;
+              }
+            }
           }
         }
       }

@@ -304,6 +304,9 @@ def main():
     dev_gt = host_gt.to(dev)
     out_keys = ("iou_labels", "iou_scores", "center", "size", "heading", "objectness")
     cabi = importlib.import_module("3dioumatch_b200._cabi") if a.impl == "b200" else None
+    if cabi and len(lanes) > 1 and not os.environ.get("B200_FPS_POLICY"):
+        # several steps share the GPU: FPS takes the launch shape with the least SM-time instead of the shortest chain
+        cabi.set_fps_policy("throughput")
 
     # ---- CUDA graphs: one captured step per lane (static input/output buffers), replayed with fresh inputs ----------
     use_graphs = (a.graphs == 1) or (a.graphs == -1 and a.impl == "b200")
@@ -433,7 +436,7 @@ def main():
                                "%d proposals, IoU labels vs %d GT slots; random-init weights, eval-mode BN" % (B, N, N_PROPOSAL, N_GT),
                    "scenes_per_gpu_per_step": B, "lanes": len(lanes), "cuda_graphs": bool(use_graphs),
                    "host_enqueue_ms_per_step": round(enqueue_ms, 3),
-                   "prefetch_fps_chain": bool(net.backbone.prefetch), "parallelism": "scene-sharded x%d, no data-path collective" % n_gpus,
+                   "fps_policy": ("throughput" if (a.impl == "b200" and len(lanes) > 1 and not os.environ.get("B200_FPS_POLICY")) else os.environ.get("B200_FPS_POLICY", "latency")), "prefetch_fps_chain": bool(net.backbone.prefetch), "parallelism": "scene-sharded x%d, no data-path collective" % n_gpus,
                    "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (N_ROTATE, N_ROTATE * B * N * 16 / 1e6),
                    "tf32": "torch defaults (cudnn conv TF32 allowed) for the torch-side 1x1 convs; all libb200pc kernels fp32",
                    "room_m": a.room,

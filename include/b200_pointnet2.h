@@ -30,6 +30,13 @@ const char *b200_last_error(void);
 /* number of kernel launches issued by this library since process start (bench.py's gpu_launches) */
 unsigned long long b200_launch_count(void);
 
+/* Launch-shape policy of furthest_point_sampling (no reference counterpart: the reference always runs one 512-thread
+ * block per scene, sampling_gpu.cu:180-230).  0 = latency (default): the cluster shape with the shortest serial chain,
+ * right for a call that runs alone on its stream.  1 = throughput: the shape with the least SM-time (fewer, fuller
+ * CTAs per scene), right when other kernels of a pipelined step share the GPU.  Results are identical (bit-exact) for
+ * every shape.  Returns the previous policy; the B200_FPS_POLICY environment variable sets the initial value.      */
+int b200pn2_fps_set_policy(int policy);
+
 /* furthest_point_sampling(points (B,N,3), nsamples) -> idx (B,m) int32
  * reference: sampling.cpp:70-91 + sampling_gpu.cu:74-234.
  * idx[b][0] = 0; tie order = (min-dist desc, bit-reversed (k mod bs) asc, k asc) with

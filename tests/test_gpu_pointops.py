@@ -135,6 +135,26 @@ def test_fps_scannet_shape_full_size(pkg, orc):
         assert d[fps[b, j]] >= d.max() * (1 - 1e-5)
 
 
+def test_fps_policy_is_result_neutral(pkg):
+    """b200pn2_fps_set_policy: the throughput launch shape (fewer, fuller CTAs per scene) returns the same indices as the
+    latency shape, on a ScanNet-sized and a SUN RGB-D-sized batch with duplicated points (exact ties)."""
+    import importlib
+    import pointnet2._ext as ext
+    cabi = importlib.import_module("3dioumatch_b200._cabi")
+    prev = cabi.set_fps_policy("latency")
+    try:
+        for (B, N, m, seed) in ((3, 40000, 2048, 4), (5, 20000, 2048, 5), (2, 2048, 1024, 6)):
+            pc = cases.cloud(seed, B, N, dup_frac=0.05)
+            t = dev(pc)
+            cabi.set_fps_policy("latency")
+            a = ext.furthest_point_sampling(t, m)
+            cabi.set_fps_policy("throughput")
+            b = ext.furthest_point_sampling(t, m)
+            assert torch.equal(a, b)
+    finally:
+        cabi.set_fps_policy(prev)
+
+
 def test_group_gather_interpolate_and_grads(pkg, orc):
     import pointnet2._ext as ext
     rng = np.random.default_rng(0)

@@ -218,6 +218,10 @@ __device__ unsigned long long g_tcp_prof[48];
 #define TP_HLAP(cat)
 #endif
 
+// MODE: row source (0 ball-query lists, 1 three-neighbour blends, 2 plain row GEMM with row output); PRE: factorised first
+// layer (rows of P + xyz FMAs + ReLU in the producers).  Compile-time so that each variant's producer only carries its own
+// registers -- the gather is register-bound (a runtime-mode kernel with one more row source measured 20 % slower).
+template <int MODE, int PRE>
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     s_scale[e] = c < p.L[l].cout ? p.L[l].scale[c] : 0.f;
     s_shift[e] = c < p.L[l].cout ? p.L[l].shift[c] : 0.f;
   }
-  for (int e = tid; e < 3 * 128; e += TP_THREADS) s_wx[e] = p.pre ? p.wx[e] : 0.f;
+  for (int e = tid; e < 3 * 128; e += TP_THREADS) s_wx[e] = PRE ? p.wx[e] : 0.f;
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       if (t < 0) break;
       int b, m0, g_here, slot, gi;
       bool valid;
-      if (p.mode == 2) {
+      if (MODE == 2) {
         // plain row GEMM (pass 1 of the factorised layer 1): tile row = point t * 128 + row of the flattened (B*N, C) input
         b = 0; m0 = 0; g_here = 1; gi = 0; slot = 0;
         valid = t * TC_ROWS + row < p.rows_total;
@@ -456,17 +460,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       }
       int src_idx = 0;
       float ctr[3] = {0.f, 0.f, 0.f};
-      if (valid && p.mode == 0) {
+      if (valid && MODE == 0) {
         src_idx = p.idx[((size_t)b * p.M + m0 + gi) * ns + slot];
         const float *c = p.new_xyz + ((size_t)b * p.M + m0 + gi) * 3;
         ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
       }
-      const float *frow = (valid && C > 0 && p.mode == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
-      if (valid && p.mode == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * C;
+      const float *frow = (valid && C > 0 && MODE == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
+      if (valid && MODE == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * C;
       float rel[3] = {0.f, 0.f, 0.f};
       const float *f3[3] = {nullptr, nullptr, nullptr};
       float wt[3] = {0.f, 0.f, 0.f};
-      if (p.mode == 1 && valid) {
+      if (MODE == 1 && valid) {
         const size_t q = ((size_t)b * p.M + m0 + gi) * ns + slot;
         for (int u = 0; u < 3; ++u) {
           f3[u] = p.feat_pm + ((size_t)b * p.N + p.idx3[q * 3 + u]) * C;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           rel[0] = p.rel3[q * 3 + 0]; rel[1] = p.rel3[q * 3 + 1]; rel[2] = p.rel3[q * 3 + 2];
         }
       }
-      if (valid && p.use_xyz && p.mode == 0) {
+      if (valid && p.use_xyz && MODE == 0) {
         const float *q = p.xyz + ((size_t)b * p.N + src_idx) * 3;
         // pointnet2_utils.py:351-353: grouped_xyz -= new_xyz ; /= radius  (x * fp32(1/r) on CUDA)
         rel[0] = __fmul_rn(__fsub_rn(q[0], ctr[0]), p.inv_r);
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int ch = kb * 32 + c * 4;
-          if (valid && p.mode == 1 && ch + 3 < C) {  // blend of the three neighbours (three_interpolate + concat)
+          if (valid && MODE == 1 && ch + 3 < C) {  // blend of the three neighbours (three_interpolate + concat)
             const float4 a0 = __ldg(reinterpret_cast<const float4 *>(f3[0] + ch));
             const float4 a1 = __ldg(reinterpret_cast<const float4 *>(f3[1] + ch));
             const float4 a2 = __ldg(reinterpret_cast<const float4 *>(f3[2] + ch));
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].y = __fmaf_rn(a2.y, wt[2], __fmaf_rn(a0.y, wt[0], __fmul_rn(a1.y, wt[1])));
             v[c].z = __fmaf_rn(a2.z, wt[2], __fmaf_rn(a0.z, wt[0], __fmul_rn(a1.z, wt[1])));
             v[c].w = __fmaf_rn(a2.w, wt[2], __fmaf_rn(a0.w, wt[0], __fmul_rn(a1.w, wt[1])));
-          } else if (valid && p.mode != 1 && p.vec_gather && ch + 3 < C) {
+          } else if (valid && MODE != 1 && p.vec_gather && ch + 3 < C) {
             v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
           } else {
             float e4[4];
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               float x = 0.f;
               if (valid) {
                 if (k < C) {
-                  x = p.mode != 1 ? frow[k]
+                  x = MODE != 1 ? frow[k]
                                   : __fmaf_rn(f3[2][k], wt[2], __fmaf_rn(f3[0][k], wt[0], __fmul_rn(f3[1][k], wt[1])));
                 } else if (p.use_xyz && k < C + 3) {
                   x = rel[k - C];
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             }
             v[c] = make_float4(e4[0], e4[1], e4[2], e4[3]);
           }
-          if (p.pre) {
+          if (PRE) {
             // factorised layer 1: v holds scale1 * (W1f * f) + shift1 of the source point (or the blend of three);
             // add the relative-xyz part of the layer and apply its ReLU (rel = 0 and v = 0 for rows past the end)
             const float4 w0 = *reinterpret_cast<const float4 *>(s_wx + ch);
@@ -656,7 +660,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 v[c * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
                 v[c * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
               }
-              if (p.rowout) {
+              if ((MODE == 2)) {
                 // plain row GEMM: affine without the ReLU, this row's 32 columns stored as one 128-byte run
                 const size_t grow = (size_t)t * TC_ROWS + row;
                 if (grow < (size_t)p.rows_total) {
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               TP_LAP(18);
             }
           }
-          if (ns > 32 && !p.units && !p.rowout) {
+          if (ns > 32 && !p.units && !(MODE == 2)) {
             TP_BEGIN();
             // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -823,14 +827,19 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
   if (force_slots >= 2 && force_slots < p.nslots) p.nslots = force_slots;
   B200_CHECK_ARG(p.nslots >= 2, "sa_forward(tc): weight ring does not fit (%d-byte slots)", p.wslot_bytes);
   const size_t smem = rest + (size_t)p.nslots * p.wslot_bytes;
-  static size_t attr = 0;
-  if (smem > attr) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sa_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  void (*kern)(const TcParams) = nullptr;
+  int variant = 0;
+  if (p.mode == 2) { kern = sa_tcp_kernel<2, 0>; variant = 4; }
+  else if (p.mode == 1) { kern = p.pre ? sa_tcp_kernel<1, 1> : sa_tcp_kernel<1, 0>; variant = 2 + (p.pre ? 1 : 0); }
+  else { kern = p.pre ? sa_tcp_kernel<0, 1> : sa_tcp_kernel<0, 0>; variant = p.pre ? 1 : 0; }
+  static size_t attr[5] = {0, 0, 0, 0, 0};
+  if (smem > attr[variant]) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[variant] = smem;
   }
   // the tile counter was zeroed in stream order by tc_pack_weights_kernel (sa_tc.cu)
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  sa_tcp_kernel<<<grid, TP_THREADS, smem, stream>>>(p);
+  kern<<<grid, TP_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_tcp_kernel");
   return 0;
 }

@@ -96,10 +96,13 @@ def test_sa_many_tiles_per_cta(orc, tr, pkg, shape):
     (2, 2048, 1024, 128, 0.4, 32, [128, 128, 256]),   # SA2-like (compacted tiles)
     (3, 1024, 333, 256, 0.8, 16, [128, 128, 128]),    # vote-aggregation-like, ragged last tile
     (2, 777, 128, 64, 0.5, 16, [96, 64, 32]),         # narrow widths, point count not a multiple of the 128-row GEMM tile
+    (2, 6000, 700, 1, 0.2, 64, [64, 64, 128]),        # SA1-like: <= 4 raw channels -> layer 1 evaluated in the gather
+    (2, 1500, 300, 3, 0.3, 16, [64, 64, 128]),        # three raw channels, uncompacted tiles
 ])
 def test_sa_first_layer_factorised_and_not(orc, tr, pkg, monkeypatch, shape, factor):
-    """B200_SA_TC_FACTOR: layer 1 as a per-point row GEMM + xyz FMAs in the gather (default) vs one GEMM per grouped row;
-    both meet the same 1e-5 bar against the fp32 reference, with and without relative-xyz channels."""
+    """B200_SA_TC_FACTOR: layer 1 as a per-point row GEMM + xyz FMAs in the gather (>= 32 feature channels) or entirely
+    in the gather (<= 4 channels) vs one GEMM per grouped row; both meet the same 1e-5 bar against the fp32 reference,
+    with and without relative-xyz channels."""
     monkeypatch.setenv("B200_SA_TC_FACTOR", factor)
     B, N, M, C, r, ns, spec = shape
     run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 31 + M, dup=0.02)

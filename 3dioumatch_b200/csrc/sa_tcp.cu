@@ -31,7 +31,7 @@
 
 namespace b200 {
 
-constexpr int TP_THREADS = 448;
+constexpr int TP_THREADS = 512;   // 16 warps: the last warpgroup is {MMA, loader, 2 idle warps that only donate registers}
 constexpr int TP_EPI = 256;     // epilogue threads (warps 0-7)
 constexpr int TP_PROD0 = 256;   // first producer thread (warps 8-11)
 constexpr int TP_MMA_WARP = 12, TP_LOAD_WARP = 13;
@@ -273,6 +273,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
+  // Register reallocation between warpgroups (the SM's register file is split per scheduler: 4 warps x 128 at launch).
+  // The MMA / loader warpgroup needs few registers; the producers (gather double buffer: 64 registers of loads in flight
+  // per buffer) take what it gives up.  Per scheduler: 2 epilogue warps x 128 + 1 producer x 200 + 1 x 56 = 512.
+  // (each setmaxnreg sits inside its role's branch, so that only that role's code is compiled against the new budget)
 #ifdef B200_TC_PROFILE
   unsigned long long tp_acc[32] = {0};
   const int tp_tile_cat = warp == TP_MMA_WARP ? 2 : (warp >= 8 ? 8 : 12);
@@ -292,6 +296,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     return t;
   };
 
+  if (warp >= 12) {
+  // last warpgroup: loader, MMA issuer and two idle warps; their registers go to the producers
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == TP_LOAD_WARP) {
     // ================= tile scheduler + weight loader (converged warp, elected lane issues) =================
     int n_pub = 0;
@@ -424,8 +431,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       }
       ++tl;
     }
+  }
   } else if (warp >= 8) {
     // ================= producers: row (tid - 256) of the tile, layer-1 A operand =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
     const int row = tid - TP_PROD0;
     const int g = row / ns;
     const int C = p.C;
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int ch = kb * 32 + c * 4;
-          if (valid && MODE == 1 && ch + 3 < C) {  // blend of the three neighbours (three_interpolate + concat)
+          if (valid && MODE == 1 && (PRE || ch + 3 < C)) {  // blend of the three neighbours (three_interpolate + concat)
             const float4 a0 = __ldg(reinterpret_cast<const float4 *>(f3[0] + ch));
             const float4 a1 = __ldg(reinterpret_cast<const float4 *>(f3[1] + ch));
             const float4 a2 = __ldg(reinterpret_cast<const float4 *>(f3[2] + ch));
@@ -501,8 +510,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].y = __fmaf_rn(a2.y, wt[2], __fmaf_rn(a0.y, wt[0], __fmul_rn(a1.y, wt[1])));
             v[c].z = __fmaf_rn(a2.z, wt[2], __fmaf_rn(a0.z, wt[0], __fmul_rn(a1.z, wt[1])));
             v[c].w = __fmaf_rn(a2.w, wt[2], __fmaf_rn(a0.w, wt[0], __fmul_rn(a1.w, wt[1])));
-          } else if (valid && MODE != 1 && p.vec_gather && ch + 3 < C) {
+          } else if (valid && MODE != 1 && (PRE || (p.vec_gather && ch + 3 < C))) {
             v[c] = __ldg(reinterpret_cast<const float4 *>(frow + ch));
+          } else if (PRE) {
+            v[c] = make_float4(0.f, 0.f, 0.f, 0.f);  // rows of P are whole 128-byte k-blocks: no scalar tail
           } else {
             float e4[4];
 #pragma unroll
@@ -514,16 +525,23 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                   x = MODE != 1 ? frow[k]
                                   : __fmaf_rn(f3[2][k], wt[2], __fmaf_rn(f3[0][k], wt[0], __fmul_rn(f3[1][k], wt[1])));
                 } else if (p.use_xyz && k < C + 3) {
-                  x = rel[k - C];
+                  x = k == C ? rel[0] : (k == C + 1 ? rel[1] : rel[2]);
                 }
               }
               e4[e] = x;
             }
             v[c] = make_float4(e4[0], e4[1], e4[2], e4[3]);
           }
-          if (PRE) {
-            // factorised layer 1: v holds scale1 * (W1f * f) + shift1 of the source point (or the blend of three);
-            // add the relative-xyz part of the layer and apply its ReLU (rel = 0 and v = 0 for rows past the end)
+        }
+      };
+      auto store_kb = [&](int kb, float4 (&v)[8]) {
+        if (PRE) {
+          // factorised layer 1, applied when the k-block is consumed (the loads stay in flight until here): v holds
+          // scale1 * (W1f * f) + shift1 of the source point (or the blend of three); add the relative-xyz part of the
+          // layer and apply its ReLU (rel = 0 and v = 0 for rows past the end)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = kb * 32 + c * 4;
             const float4 w0 = *reinterpret_cast<const float4 *>(s_wx + ch);
             const float4 w1 = *reinterpret_cast<const float4 *>(s_wx + 128 + ch);
             const float4 w2 = *reinterpret_cast<const float4 *>(s_wx + 256 + ch);
@@ -533,8 +551,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].w = fmaxf(__fmaf_rn(w2.w, rel[2], __fmaf_rn(w1.w, rel[1], __fmaf_rn(w0.w, rel[0], v[c].w))), 0.f);
           }
         }
-      };
-      auto store_kb = [&](const float4 (&v)[8]) {
         TPW(9, &empty_a[sa], pa ^ 1u);
         uint8_t *a_hi = R1 + sa * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
 #pragma unroll
@@ -557,10 +573,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       load_kb(0, va);
       for (int kb = 0; kb < nkb1; kb += 2) {
         if (kb + 1 < nkb1) load_kb(kb + 1, vb);
-        store_kb(va);
+        store_kb(kb, va);
         if (kb + 1 < nkb1) {
           if (kb + 2 < nkb1) load_kb(kb + 2, va);
-          store_kb(vb);
+          store_kb(kb + 1, vb);
         }
       }
     }

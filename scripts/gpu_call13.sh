@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-O=gpurun_out/c15; mkdir -p $O
+O=gpurun_out/c16; mkdir -p $O
 echo "== parity"; timeout 900 python -m pytest tests/test_gpu_sa_fused.py tests/test_gpu_harness_vs_reference.py -m gpu -x -q 2>&1 | tail -4 | tee $O/pytest.log
 run() { name=$1; shift; env "$@" timeout 600 python bench.py $Q > $O/bench_$name.json 2> $O/bench_$name.err; tail -2 $O/bench_$name.err; python - <<PY
 import json

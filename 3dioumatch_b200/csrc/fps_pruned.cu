@@ -317,7 +317,8 @@ typedef void (*fpp_fn)(int, int, int, int, const float *, const int *, int32_t *
 bool fps_pruned_wanted(int B, int N, int m) {
   const char *e = getenv("B200_FPS_PRUNE");
   if (!e || atoi(e) == 0 || m < 2 || B > 65535) return false;
-  return N >= 256;
+  const char *mn = getenv("B200_FPS_PRUNE_MIN_N");  // only clouds of at least this many points (default 256)
+  return N >= (mn ? atoi(mn) : 256);
 }
 
 // returns 0 on success, -1 when the shape is not handled here (the caller falls back to fps.cu), >0 on error

@@ -493,7 +493,7 @@ def main():
                 ncu_frac = None
                 try:  # time-weighted sm__pipe_tensor_cycles_active of the sa_tcp_kernel launches in the committed capture
                     import csv
-                    rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1b_ncu_full_kernels.csv"))))
+                    rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1c_ncu_full_kernels.csv"))))
                     hdr = rows[0]
                     ti = [i for i, h in enumerate(hdr) if h.startswith("gpu__time_duration")][0]
                     pi = [i for i, h in enumerate(hdr) if h.startswith("sm__pipe_tensor_cycles_active")][0]
@@ -509,7 +509,7 @@ def main():
                     "note": "achieved = REFERENCE-EQUIVALENT fp32 FLOPs (every nsample row of every centre) / time: the kernel "
                             "skips duplicated neighbour rows, so this is delivered work, not tensor-pipe work; each executed "
                             "product costs 3 kind::tf32 MMAs (split precision for the 1e-5 bar).  frac = tensor-pipe active "
-                            "fraction measured by ncu (profiles/r1b_ncu_full_kernels.csv, time-weighted over the sa_tcp_kernel "
+                            "fraction measured by ncu (profiles/r1c_ncu_full_kernels.csv, time-weighted over the sa_tcp_kernel "
                             "launches); peak = dense TF32 = half the measured bf16 cuBLAS figure in MEASURED_PEAKS.json"}
         # ---- configs[2]: 256 x 256 rotated 3D IoU + NMS (device-resident boxes, CUDA events) ------------------------
         try:

@@ -31,6 +31,13 @@ PROTOTYPES = {
     "b200pn2_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p]),
+    "b200pn2_scatter_det_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "b200pn2_gather_points_grad_det": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_size_t, c_void_p]),
+    "b200pn2_group_points_grad_det": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_size_t, c_void_p]),
+    "b200pn2_three_interpolate_grad_det": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_size_t, c_void_p]),
     "b200pn2_sa_forward_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "b200pn2_sa_forward": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p, c_void_p,

@@ -38,6 +38,19 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
 
 
+def deterministic():
+    """True when gradients must be bit-reproducible: torch.use_deterministic_algorithms(True) or B200_DETERMINISTIC=1.
+    The *_grad entries then run the sorted-segment kernels (csrc/scatter_det.cu) instead of the reference's atomicAdd
+    scatter (sampling_gpu.cu:39-52, group_points_gpu.cu:48-68, interpolate_gpu.cu:121-148)."""
+    import os
+    return torch.are_deterministic_algorithms_enabled() or os.environ.get("B200_DETERMINISTIC") == "1"
+
+
+def _det_workspace(B, targets, entries, device):
+    nbytes = int(_L().b200pn2_scatter_det_workspace(int(B), int(targets), int(entries)))
+    return torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=device), nbytes
+
+
 def furthest_point_sampling(points, nsamples):
     """(B,N,3) f32 -> (B,nsamples) int32   [sampling.cpp:70-91]"""
     _contig(points, "points"); _is_float(points, "points"); _cuda(points, None)
@@ -70,8 +83,13 @@ def gather_points_grad(grad_out, idx, n):
     B, C, m = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        cabi.check(_L().b200pn2_gather_points_grad(B, C, int(n), m, _p(grad_out), _p(idx), _p(out), stream_ptr()),
-                   "gather_points_grad")
+        if deterministic():
+            ws, nbytes = _det_workspace(B, n, m, grad_out.device)
+            cabi.check(_L().b200pn2_gather_points_grad_det(B, C, int(n), m, _p(grad_out), _p(idx), _p(out), _p(ws), nbytes,
+                                                           stream_ptr()), "gather_points_grad_det")
+        else:
+            cabi.check(_L().b200pn2_gather_points_grad(B, C, int(n), m, _p(grad_out), _p(idx), _p(out), stream_ptr()),
+                       "gather_points_grad")
     return out
 
 
@@ -113,8 +131,13 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     B, C, n = grad_out.shape
     out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        cabi.check(_L().b200pn2_three_interpolate_grad(B, C, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(out),
-                                                       stream_ptr()), "three_interpolate_grad")
+        if deterministic():
+            ws, nbytes = _det_workspace(B, m, 3 * n, grad_out.device)
+            cabi.check(_L().b200pn2_three_interpolate_grad_det(B, C, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(out),
+                                                               _p(ws), nbytes, stream_ptr()), "three_interpolate_grad_det")
+        else:
+            cabi.check(_L().b200pn2_three_interpolate_grad(B, C, n, int(m), _p(grad_out), _p(idx), _p(weight), _p(out),
+                                                           stream_ptr()), "three_interpolate_grad")
     return out
 
 
@@ -150,8 +173,13 @@ def group_points_grad(grad_out, idx, n):
     B, C, M, ns = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        cabi.check(_L().b200pn2_group_points_grad(B, C, int(n), M, ns, _p(grad_out), _p(idx), _p(out), stream_ptr()),
-                   "group_points_grad")
+        if deterministic():
+            ws, nbytes = _det_workspace(B, n, M * ns, grad_out.device)
+            cabi.check(_L().b200pn2_group_points_grad_det(B, C, int(n), M, ns, _p(grad_out), _p(idx), _p(out), _p(ws), nbytes,
+                                                          stream_ptr()), "group_points_grad_det")
+        else:
+            cabi.check(_L().b200pn2_group_points_grad(B, C, int(n), M, ns, _p(grad_out), _p(idx), _p(out), stream_ptr()),
+                       "group_points_grad")
     return out
 
 

@@ -84,6 +84,22 @@ int b200pn2_three_interpolate(int B, int C, int m, int n, const float *points, c
 int b200pn2_three_interpolate_grad(int B, int C, int n, int m, const float *grad_out, const int32_t *idx,
                                    const float *weight, float *grad_points, b200_stream_t stream);
 
+/* ---- deterministic gradients (next-row n4 of SURVEY.md section 8f) -------------------------------------------------
+ * Same results as the three *_grad entries above up to fp32 summation order, but the order is fixed: every target
+ * point sums the entries that feed it in ascending entry position (the order of a sequential loop), so the output is
+ * bit-reproducible -- the reference's atomicAdd kernels (sampling_gpu.cu:39-52, group_points_gpu.cu:48-68,
+ * interpolate_gpu.cu:121-148) are not.  `workspace` >= b200pn2_scatter_det_workspace(B, targets per scene, entries per
+ * scene) bytes of device memory: targets = N (gather, group) or m (interpolate); entries = m (gather), M*ns (group),
+ * 3*n (interpolate).                                                                                              */
+size_t b200pn2_scatter_det_workspace(int B, int n_targets, int entries_per_scene);
+int b200pn2_gather_points_grad_det(int B, int C, int N, int m, const float *grad_out, const int32_t *idx,
+                                   float *grad_points, void *workspace, size_t workspace_bytes, b200_stream_t stream);
+int b200pn2_group_points_grad_det(int B, int C, int N, int M, int ns, const float *grad_out, const int32_t *idx,
+                                  float *grad_points, void *workspace, size_t workspace_bytes, b200_stream_t stream);
+int b200pn2_three_interpolate_grad_det(int B, int C, int n, int m, const float *grad_out, const int32_t *idx,
+                                       const float *weight, float *grad_points, void *workspace,
+                                       size_t workspace_bytes, b200_stream_t stream);
+
 /* ---- fused set-abstraction forward (the wide entry; no single reference counterpart) ------------
  * Replaces the sequence  ball_query -> group_points(xyz) -> (-centre, *1/r) -> group_points(features)
  * -> concat -> SharedMLP (1x1 conv + eval-mode BN + ReLU, up to 3 layers) -> max over nsample

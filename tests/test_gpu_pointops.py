@@ -185,6 +185,56 @@ def test_group_gather_interpolate_and_grads(pkg, orc):
     assert np.allclose(got, orc.three_interpolate_grad(go3, tidx, w, m), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(3, 37, 500, 64, 16), (2, 9, 4000, 700, 32), (1, 5, 64, 200, 8)])
+def test_deterministic_gradients_bit_exact(pkg, orc, monkeypatch, shape):
+    """B200_DETERMINISTIC=1 / torch.use_deterministic_algorithms: the sorted-segment gradient kernels sum every target's
+    entries in ascending entry position -- the order of the oracle's sequential loops -- so the three gradients equal the
+    CPU oracle bit for bit (many duplicates per target, empty targets, heavy collisions in the last shape) and repeat."""
+    import pointnet2._ext as ext
+    monkeypatch.setenv("B200_DETERMINISTIC", "1")
+    B, C, N, M, ns = shape
+    rng = np.random.default_rng(sum(shape))
+    idx = rng.integers(0, N, (B, M, ns)).astype(np.int32)
+    idx[:, : M // 2] = rng.integers(0, max(N // 50, 1), (B, M // 2, ns))          # pile-ups on a few targets
+    go = rng.standard_normal((B, C, M, ns)).astype(np.float32)
+    a = ext.group_points_grad(dev(go), dev(idx), N)
+    assert np.array_equal(a.cpu().numpy(), orc.group_points_grad(go, idx, N))
+    assert torch.equal(a, ext.group_points_grad(dev(go), dev(idx), N))
+    gi = rng.integers(0, N, (B, M)).astype(np.int32)
+    go2 = rng.standard_normal((B, C, M)).astype(np.float32)
+    assert np.array_equal(ext.gather_points_grad(dev(go2), dev(gi), N).cpu().numpy(), orc.gather_points_grad(go2, gi, N))
+    n, m = M * 3 + 1, max(N // 7, 3)
+    tidx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = rng.random((B, n, 3)).astype(np.float32)
+    w /= w.sum(2, keepdims=True)
+    go3 = rng.standard_normal((B, C, n)).astype(np.float32)
+    got = ext.three_interpolate_grad(dev(go3), dev(tidx), dev(w), m).cpu().numpy()
+    assert np.array_equal(got, orc.three_interpolate_grad(go3, tidx, w, m))
+
+
+def test_deterministic_flag_reaches_autograd(pkg):
+    """torch.use_deterministic_algorithms(True) routes the autograd Functions' backward through the deterministic
+    kernels: two backward passes of a grouping + interpolation graph give identical gradients."""
+    import pointnet2.pointnet2_utils as U
+    torch.manual_seed(0)
+    feats = torch.randn(2, 16, 300, device="cuda", requires_grad=True)
+    idx = torch.randint(0, 12, (2, 200, 16), device="cuda", dtype=torch.int32)     # heavy collisions
+    known = torch.randn(2, 16, 40, device="cuda", requires_grad=True)
+    tidx = torch.randint(0, 40, (2, 300, 3), device="cuda", dtype=torch.int32)
+    w = torch.rand(2, 300, 3, device="cuda")
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        grads = []
+        for _ in range(2):
+            feats.grad = known.grad = None
+            (U.grouping_operation(feats, idx).square().sum() + U.three_interpolate(known, tidx, w).square().sum()).backward()
+            grads.append((feats.grad.clone(), known.grad.clone()))
+        assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+    finally:
+        torch.use_deterministic_algorithms(prev)
+
+
 def test_autograd_functions(pkg):
     """pointnet2_utils Functions: gradients flow through gather/group/interpolate (torch.autograd.gradcheck-style
     directional check in fp32)."""

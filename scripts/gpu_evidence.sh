@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-1c evidence: full GPU suite, smoke, default bench, reference arm, ncu launch list, ncu full capture
 cd "$(dirname "$0")/.."
-O=gpurun_out/c17; mkdir -p $O
+O=gpurun_out/evidence; mkdir -p $O
 echo "== full gpu suite"; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/pytest_gpu.log
 echo "== smoke"; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $O/smoke.log
 echo "== bench (default flags)"; timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; head -c 400 $O/bench.json; echo; tail -3 $O/bench.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-O=gpurun_out/c18; mkdir -p $O
+O=gpurun_out/fps_variants; mkdir -p $O
 run() { name=$1; shift; env "$@" timeout 600 python bench.py $Q > $O/bench_$name.json 2> $O/bench_$name.err; tail -2 $O/bench_$name.err; python - <<PY
 import json
 try:

@@ -89,3 +89,14 @@ def test_iou_cpu_entry_and_wrappers(pkg, orc):
     with pytest.raises(RuntimeError, match="CUDA"):                   # iou3d_nms.cpp:14-19, without exit(-1)
         from pcdet.ops.iou3d_nms import iou3d_nms_cuda
         iou3d_nms_cuda.boxes_overlap_bev_gpu(torch.zeros(1, 7), torch.zeros(1, 7), torch.zeros(1, 1))
+
+
+def test_fps_policy_knob_roundtrip(pkg):
+    """b200pn2_fps_set_policy is host state only (no CUDA call): returns the previous policy, clamps unknown values."""
+    import importlib
+    cabi = importlib.import_module("3dioumatch_b200._cabi")
+    first = cabi.set_fps_policy("throughput")
+    assert first in ("latency", "throughput")
+    assert cabi.set_fps_policy("latency") == "throughput"
+    assert cabi.lib().b200pn2_fps_set_policy(7) == 0          # 7 is not a policy: stored as latency (0)
+    assert cabi.lib().b200pn2_fps_set_policy(0 if first == "latency" else 1) == 0

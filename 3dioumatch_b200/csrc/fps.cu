@@ -94,28 +94,47 @@ __device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned remot
 // Per iteration:  PPT branch-free distance updates -> warp arg-max (2 x redux.sync) -> CTA arg-max through shared
 // memory -> [cluster] each CTA pushes its 32-byte record into every peer's shared memory with st.async, which also
 // signals the peer's mbarrier (complete_tx); every thread waits on its own CTA's mbarrier.  No cluster-wide barrier.
-template <int THREADS, int PPT, int MINB = 1>
+// GROUPS = 2: the CTA is two independent 256-thread groups, each working on its OWN scene (own registers, coordinate
+// table, records, mbarriers, and a named barrier instead of __syncthreads).  An iteration is half issue-bound update and
+// half reduction/exchange latency; two scenes on one SM fill each other's latency, which two co-resident CTAs would too
+// -- but the block scheduler spreads CTAs over free SMs first, so only a single CTA guarantees the sharing.
+template <int THREADS, int PPT, int MINB = 1, int GROUPS = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
-fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
-  constexpr int NWARP = THREADS / 32;
-  extern __shared__ float s_xyz[];  // [PPT][THREADS][3]
+fps_cluster_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
+  constexpr int GT = THREADS / GROUPS;  // threads per scene in this CTA
+  constexpr int NWARP = GT / 32;
+  extern __shared__ float s_xyz_all[];  // [GROUPS][PPT][GT][3]
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned CS = cluster.num_blocks();  // power of two
   const unsigned rank = cluster.block_rank();
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = (int)CS * THREADS;  // threads per scene, a power of two
+  const int grp = GROUPS > 1 ? (int)threadIdx.x / GT : 0;
+  const int b = blockIdx.y * GROUPS + grp;
+  const bool live = b < B;  // an odd batch leaves the last CTA's second group without a scene
+  const int tid = GROUPS > 1 ? (int)threadIdx.x % GT : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = (int)CS * GT;  // threads per scene, a power of two
   const int log2T = 31 - __clz(T);
-  const int g = (int)rank * THREADS + tid;
+  const int g = (int)rank * GT + tid;
+  float *s_xyz = s_xyz_all + (size_t)grp * PPT * GT * 3;
 
-  const float *pts = xyz + (size_t)b * N * 3;
-  int32_t *out = idx + (size_t)b * m;
+  const float *pts = xyz + (size_t)(live ? b : 0) * N * 3;
+  int32_t *out = idx + (size_t)(live ? b : 0) * m;
 
-  __shared__ int s_v[2][NWARP];
-  __shared__ unsigned s_key[2][NWARP];
-  __shared__ int s_k[2][NWARP];
-  __shared__ FpsRecord s_slot[2][16];
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ int s_v_all[GROUPS][2][NWARP];
+  __shared__ unsigned s_key_all[GROUPS][2][NWARP];
+  __shared__ int s_k_all[GROUPS][2][NWARP];
+  __shared__ FpsRecord s_slot_all[GROUPS][2][16];
+  __shared__ __align__(8) unsigned long long s_bar_all[GROUPS][2];
+  int (*s_v)[NWARP] = s_v_all[grp];
+  unsigned (*s_key)[NWARP] = s_key_all[grp];
+  int (*s_k)[NWARP] = s_k_all[grp];
+  FpsRecord (*s_slot)[16] = s_slot_all[grp];
+  unsigned long long *s_bar = s_bar_all[grp];
+  auto group_sync = [&]() {
+    if (GROUPS > 1)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GT) : "memory");
+    else
+      __syncthreads();
+  };
 
   if (CS > 1) {
     if (tid == 0) {
@@ -131,7 +150,7 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
     const int k = g + p * T;
-    if (k < N) {
+    if (k < N && live) {
       px[p] = pts[(size_t)k * 3 + 0];
       py[p] = pts[(size_t)k * 3 + 1];
       pz[p] = pts[(size_t)k * 3 + 2];
@@ -143,7 +162,7 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
       px[p] = py[p] = pz[p] = 0.f;
       pt[p] = -1.0f;
     }
-    float *sp = s_xyz + (size_t)(p * THREADS + tid) * 3;
+    float *sp = s_xyz + (size_t)(p * GT + tid) * 3;
     sp[0] = px[p]; sp[1] = py[p]; sp[2] = pz[p];
   }
   __syncthreads();
@@ -157,20 +176,20 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
   // first strict maximum is already the reference's choice; otherwise exact ties inside a thread need the keys.
   const bool thread_ties = ((unsigned)T & bsmask) != 0u;
   auto coords_of = [&](int k, float &x, float &y, float &z) {  // k owned by this CTA
-    const int p = k >> log2T, t = (k & (T - 1)) - (int)rank * THREADS;
-    const float *sp = s_xyz + (size_t)(p * THREADS + t) * 3;
+    const int p = k >> log2T, t = (k & (T - 1)) - (int)rank * GT;
+    const float *sp = s_xyz + (size_t)(p * GT + t) * 3;
     x = sp[0]; y = sp[1]; z = sp[2];
   };
 
   const float x0 = pts[0], y0 = pts[1], z0 = pts[2];
   float cx = x0, cy = y0, cz = z0;  // idx[0] = 0 (:89-92)
-  if (rank == 0 && tid == 0) out[0] = 0;
+  if (rank == 0 && tid == 0 && live) out[0] = 0;
 
 #ifdef B200_FPS_PROFILE
   unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 #endif
-  for (int j = 1; j < m; ++j) {
+  for (int j = 1; j < m && live; ++j) {
     const int par = j & 1;
     if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[par], CS * (unsigned)sizeof(FpsRecord));
     // ---- distance update + per-thread arg-max (branch-free; first strict maximum in slot order) ----------
@@ -240,7 +259,7 @@ fps_cluster_kernel(int N, int m, int L, const float *__restrict__ xyz, int32_t *
         s_key[par][warp] = bkey;
         s_k[par][warp] = bk;
       }
-      __syncthreads();
+      group_sync();
       // every warp redundantly reduces the NWARP records (no second barrier needed)
       const int cv = lane < NWARP ? s_v[par][lane] : (int)0x80000000;
       const unsigned ckey = lane < NWARP ? s_key[par][lane] : 0xffffffffu;
@@ -347,7 +366,7 @@ bool fps_pruned_wanted(int B, int N, int m);
 int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx, cudaStream_t stream);
 
 // ---- host side -----------------------------------------------------------------------------------
-typedef void (*fps_fn)(int, int, int, const float *, int32_t *);
+typedef void (*fps_fn)(int, int, int, int, const float *, int32_t *);
 
 template <int THREADS, int MINB = 1>
 static fps_fn pick_ppt(int ppt, int *ppt_out) {
@@ -364,10 +383,15 @@ static fps_fn pick_ppt(int ppt, int *ppt_out) {
   return nullptr;
 }
 
-// two co-resident CTAs per SM (128 registers per thread): the latency-bound reduction/exchange half of one CTA's
-// iteration runs under the issue-bound update half of the other, so a scene costs about half the SM-time.
-static fps_fn pick_kernel2(int threads, int ppt, int *ppt_out) {
-  if (threads == 256 && ppt >= 8) return pick_ppt<256, 2>(ppt, ppt_out);
+// two scenes per 512-thread CTA (256 threads each; fps_cluster_kernel<512, P, 1, 2>)
+static fps_fn pick_grouped(int ppt, int *ppt_out) {
+#define B200_FPS_CASE(P)                      \
+  if (ppt <= P) {                             \
+    *ppt_out = P;                             \
+    return fps_cluster_kernel<512, P, 1, 2>;  \
+  }
+  B200_FPS_CASE(8) B200_FPS_CASE(12) B200_FPS_CASE(16) B200_FPS_CASE(20)
+#undef B200_FPS_CASE
   *ppt_out = 0;
   return nullptr;
 }
@@ -452,8 +476,10 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
   // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
   // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.
-  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0, env_pack = 0;
+  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0, env_pack = 0, env_groups = -1;
   if (env_cs < 0) {
+    const char *eg = getenv("B200_FPS_GROUPS");  // 1: allow two scenes per CTA (fps_cluster_kernel<512, P, 1, 2>)
+    env_groups = eg ? atoi(eg) : 0;
     const char *ep = getenv("B200_FPS_PACK");  // 1: two CTAs per SM for the large-cloud shapes (pick_kernel2)
     env_pack = ep ? atoi(ep) : 0;
     const char *e = getenv("B200_FPS_CLUSTER");
@@ -467,7 +493,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   const int force_cs = N >= env_min_n ? env_cs : 0, force_threads = N >= env_min_n ? env_threads : 0;
   const int sms = num_sms();
   const bool throughput = fps_policy() == 1;
-  int best_cs = 0, best_ppt = 0, threads = 0;
+  int best_cs = 0, best_ppt = 0, threads = 0, best_groups = 1;
   fps_fn best_fn = nullptr;
   double best_cost = 1e300;
   const int cs_list[5] = {1, 2, 4, 8, 16};
@@ -484,8 +510,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       if (((cs * th) % bs) != 0 && force_threads <= 0 && force_cs <= 0) continue;
       const int need = ceil_div(N, cs * th);
       int ppt = 0;
-      fps_fn fn = env_pack ? pick_kernel2(th, need, &ppt) : nullptr;
-      if (!fn) fn = pick_kernel(th, need, &ppt);
+      fps_fn fn = pick_kernel(th, need, &ppt);
       if (!fn) continue;
       const size_t smem = sizeof(float) * 3 * (size_t)ppt * th;
       if (smem > 200 * 1024) continue;
@@ -509,13 +534,40 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       // latency policy: serial chain length; throughput policy: SM-cycles per scene (cs CTAs hold an SM each)
       const double cost = throughput ? waves * iter * cs : waves * iter;
       if (cost < best_cost) {
-        best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th;
+        best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th; best_groups = 1;
+      }
+      // two scenes per CTA (256 threads each): the pair costs one CTA-iteration of ~1.25x the single-scene length
+      // Measured (B=8, N=40000): 2.50 ms for the paired shape against 2.27 ms for one scene per 512-thread CTA on the
+      // same 32 SMs -- at 16 warps the SM is issue-bound (~300 instructions per warp-iteration at IPC 0.6), not
+      // latency-bound, so a second scene has no idle slots to fill.  Bit-exact, kept opt-in (B200_FPS_GROUPS=1).
+      const bool groups_ok = env_groups == 1;
+      if (groups_ok && th == 256 && B >= 2 && N >= 8192 && !ties) {
+        int gppt = 0;
+        fps_fn gfn = pick_grouped(need, &gppt);
+        const size_t gsmem = 2 * sizeof(float) * 3 * (size_t)gppt * 256;
+        if (gfn && gsmem <= 200 * 1024 &&
+            cudaFuncSetAttribute((void *)gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem) == cudaSuccess &&
+            (cs <= 8 ||
+             cudaFuncSetAttribute((void *)gfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+          const int gconc = cs == 1 ? sms : max_clusters(gfn, 512, cs, gsmem);
+          if (gconc > 0) {
+            const int gwaves = ceil_div(ceil_div(B, 2), gconc);
+            const double giter = 1.25 * (10.5 * gppt * 2 + 120.0 + 120.0 + 6.0 * 8 + (cs > 1 ? 620.0 : 0.0) +
+                                         (cs > 8 ? 260.0 : 0.0));
+            const double gcost = throughput ? gwaves * giter * cs / 2.0 : gwaves * giter;
+            if (gcost < best_cost) {
+              best_cost = gcost; best_cs = cs; best_ppt = gppt; best_fn = gfn; threads = 512; best_groups = 2;
+            }
+          }
+        } else {
+          cudaGetLastError();
+        }
       }
     }
   }
   if (debug)
-    fprintf(stderr, "[b200 fps] B=%d N=%d m=%d -> cluster=%d threads=%d ppt=%d (model %.0f cycles/iter)\n", B, N, m,
-            best_cs, threads, best_ppt, best_cost);
+    fprintf(stderr, "[b200 fps] B=%d N=%d m=%d -> cluster=%d threads=%d ppt=%d scenes/CTA=%d (model cost %.0f)\n", B, N, m,
+            best_cs, threads, best_ppt, best_groups, best_cost);
 
   if (!best_fn) {
     // cloud too large for the register-resident kernel
@@ -526,9 +578,9 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   }
 
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(best_cs, B, 1);
+  cfg.gridDim = dim3(best_cs, ceil_div(B, best_groups), 1);
   cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = sizeof(float) * 3 * (size_t)best_ppt * threads;
+  cfg.dynamicSmemBytes = sizeof(float) * 3 * (size_t)best_ppt * threads;  // both groups' coordinate tables
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -537,7 +589,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, best_fn, N, m, L, xyz, idx));
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, best_fn, B, N, m, L, xyz, idx));
   B200_LAUNCH_OK("fps_cluster_kernel");
   return 0;
 }

@@ -29,11 +29,12 @@ det_key_kernel(long long total, int E, int Ntgt, const int32_t *__restrict__ idx
 
 // seg_start / seg_end are zero-filled first: a target nobody points at keeps the empty segment [0, 0)
 __global__ void __launch_bounds__(SD_THREADS)
-det_bounds_kernel(long long total, const unsigned *__restrict__ keys, int *__restrict__ seg_start,
+det_bounds_kernel(long long total, unsigned nseg, const unsigned *__restrict__ keys, int *__restrict__ seg_start,
                   int *__restrict__ seg_end) {
   const long long i = (long long)blockIdx.x * SD_THREADS + threadIdx.x;
   if (i >= total) return;
   const unsigned k = keys[i];
+  if (k >= nseg) return;  // an index outside [0, N) of the last scene: never written out of bounds (undefined in the reference)
   if (i == 0 || keys[i - 1] != k) seg_start[k] = (int)i;
   if (i == total - 1 || keys[i + 1] != k) seg_end[k] = (int)i + 1;
 }
@@ -121,7 +122,7 @@ static int det_scatter(const char *what, int B, int C, int Ntgt, int E, int per_
                                                end_bit_for((unsigned long long)B * Ntgt), stream));
   count_launch(3);
   B200_CUDA_OK(cudaMemsetAsync(seg_start, 0, (L.cub - L.seg_start), stream));  // seg_start and seg_end are adjacent
-  det_bounds_kernel<<<blocks, SD_THREADS, 0, stream>>>(total, keys_out, seg_start, seg_end);
+  det_bounds_kernel<<<blocks, SD_THREADS, 0, stream>>>(total, (unsigned)B * (unsigned)Ntgt, keys_out, seg_start, seg_end);
   B200_LAUNCH_OK("det_bounds_kernel");
   dim3 grid(ceil_div(Ntgt, SD_THREADS), ceil_div(C, SD_CCHUNK), B);
   if (weight)

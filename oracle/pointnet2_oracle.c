@@ -16,7 +16,7 @@
  *   - compile this file with -ffp-contract=off so gcc adds no contraction.
  *
  * Parity status: pinned on the GPU box against the reference's own CUDA
- * extension built from /root/reference into oracle/_ref (tests/test_ref_cuda.py)
+ * extension built from /root/reference into oracle/_ref (tests/test_gpu_ref_cuda.py)
  * and against tests/golden/ vectors generated from that extension.
  */
 #include <math.h>

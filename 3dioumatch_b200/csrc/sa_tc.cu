@@ -651,12 +651,18 @@ static int sa_tc_launch_core(int B, int N, int M, int C, float radius, int nsamp
       float *P = reinterpret_cast<float *>(packed + counter_off + 2048 + unit_bytes);
       g.packed = packed; g.out_pm = P;
       const int rc1 = sa_tcp_launch(g, counters + 1, nullptr, stream);  // pass 1: P = scale1 * (W1f * f) + shift1
-      if (rc1 != 0) return rc1;
+      if (rc1 != 0) {
+        cudaFreeAsync(packed, stream);
+        return rc1;
+      }
       p.feat_pm = P; p.wx = wx;
     }
     const int rc = sa_tcp_launch(p, counters, unit_bytes ? reinterpret_cast<int *>(packed + counter_off + 2048) : nullptr,
                                  stream);
-    if (rc != 0) return rc;
+    if (rc != 0) {
+      cudaFreeAsync(packed, stream);
+      return rc;
+    }
     B200_CUDA_OK(cudaFreeAsync(packed, stream));
     return 0;
   }

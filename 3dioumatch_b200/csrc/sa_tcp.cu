@@ -4,7 +4,7 @@
 // with fp32 accumulation in TMEM -> max over nsample; pointnet2_modules.py:215-277, pytorch_utils.py:14-39), different
 // schedule.  One CTA per SM for the whole launch; tiles (128 grouped rows) come from an atomic counter, so a CTA that
 // becomes resident late (the SMs are shared with the long-running FPS cluster of the next step) finds the queue
-// empty instead of holding up the launch.  Fourteen warps:
+// empty instead of holding up the launch.  Sixteen warps (fourteen working; see the register reallocation in the kernel):
 //   warps 0-7   epilogue : two warpgroups, alternate 32-column chunks.  TMEM -> scale/shift/ReLU -> hi/lo split ->
 //                          swizzled shared memory (hidden layers); final layer: max over nsample by a butterfly
 //                          transpose-reduce in registers (warp shuffles; no slab, no CTA barrier per chunk)
@@ -14,13 +14,16 @@
 //                          uniform registers (the one-thread branch of sa_tc_kernel compiled to a 7-R2UR waterfall loop
 //                          per MMA, ~150 cycles of issue per 64-cycle MMA: measured with scripts/tcp_profile.py)
 //   warp  13    loader   : tile scheduler (atomicAdd + shared-memory tile ring, one tile ahead) and the weight stream
-//                          (cp.async.bulk ring of 4 or 8 half stages, continuous across tiles)
+//                          (cp.async.bulk ring of up to 8 half stages, continuous across layers and tiles)
+//   warps 14-15 idle     : complete the last warpgroup, whose registers (setmaxnreg.dec) go to the producers
+// The kernel is compiled per row source and first-layer mode (template <MODE, PRE>): ball-query lists, three-neighbour
+// blends (GridConv sampler) or plain rows (the per-point GEMM of a factorised first layer, sa_tc.cuh).
 // TMEM (512 columns) is split in two 256-column regions that swap roles every tile: one holds the accumulators
 // (products in [0,128), split-precision corrections in [128,256)), the other the hidden activations X_hi | X_lo, which
 // the epilogue writes with tcgen05.st and the next layer's MMAs read as their A operand straight from tensor memory
 // (measured: 70 cycles per 128x128x8 TF32 MMA with A in TMEM vs 86 from shared memory, scripts/tc_rate.py).  Hidden
-// activations therefore never touch shared memory: the 128 KB they used to occupy is a 4-stage ring for the layer-1
-// operand, so the gather of tile i+1 runs completely under the MMAs of tile i; and because the regions swap, the final
+// activations therefore never touch shared memory: the 128 KB they used to occupy is a 3-stage ring for the layer-1
+// operand plus a deeper weight ring, so the gather of tile i+1 runs completely under the MMAs of tile i; and because the regions swap, the final
 // epilogue of tile i drains its accumulators while tile i+1's layer-1 MMAs already fill the other region.
 #include <stdlib.h>
 

@@ -56,3 +56,22 @@ def test_two_gpu_line_scales():
     p = _line("r1c_bench_1gpu.json")
     assert d["n_gpus"] == 2 and d["scaling"] == "weak"
     assert d["value"] > 1.8 * p["value"]     # scene-sharded, no data-path collective
+
+
+def test_sa_hbm_view_on_the_committed_breakdown():
+    """bench.sa_hbm_view (pure function): fused-bytes and unfused-equivalent HBM views of the SA launches."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    d = _line("r1c_bench_1gpu.json")
+    sa = {k: v for k, v in d["breakdown_ms"].items() if k.startswith("sa_forward")}
+    assert len(sa) == 5
+    v = bench.sa_hbm_view(sa, d["roofline"]["peak"], d["config"]["scenes_per_gpu_per_step"])
+    assert v["bound"] == "hbm" and abs(v["frac"] - v["achieved"] / v["peak"]) < 1e-3
+    u = v["unfused_equivalent"]
+    assert abs(u["gb_per_step"] - 1.48 * 8) < 0.05           # 1.47-1.48 GB per scene (BASELINE.md section 2)
+    assert u["frac"] > 1.0                                    # the fused layers beat the unfused pipeline's HBM bound
+    # unknown shapes: the fused-bytes view only
+    w = bench.sa_hbm_view({"sa_forward[N=9,M=3,ns=8]": {"ms": 0.1, "calls_per_step": 1, "alg_bytes": 1000}}, 6000.0, 1)
+    assert "unfused_equivalent" not in w

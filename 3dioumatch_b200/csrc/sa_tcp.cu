@@ -311,8 +311,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       TPW(0, &tq_empty[slot], (uint32_t)(((n_pub / TP_TQ) & 1) ^ 1));
       int t = 0;
       if (lane == 0) {
-        t = atomicAdd(p.tile_counter, 1);
-        if (t >= total_tiles) t = -1;
+        if (MODE == 2 && n_pub >= 2) {
+          // single-layer row GEMM: a CTA takes at most two tiles, one per TMEM accumulator region.  A third would
+          // reuse the first one's region, and with one layer there is no hidden hand-off that orders its MMAs after
+          // that tile's epilogue (the launcher sizes the grid so that two per CTA cover every tile).
+          t = -1;
+        } else {
+          t = atomicAdd(p.tile_counter, 1);
+          if (t >= total_tiles) t = -1;
+        }
         tq_tile[slot] = t;
         tc::mbar_arrive(&tq_full[slot]);  // release: the tile id is visible to the waiters
       }
@@ -857,7 +864,8 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
     attr[variant] = smem;
   }
   // the tile counter was zeroed in stream order by tc_pack_weights_kernel (sa_tc.cu)
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (p.mode == 2 && 2 * grid < p.total_tiles) grid = ceil_div(p.total_tiles, 2);  // at most two tiles per CTA (see publish())
   kern<<<grid, TP_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_tcp_kernel");
   return 0;

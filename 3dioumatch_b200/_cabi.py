@@ -45,6 +45,22 @@ PROTOTYPES = {
     "b200pn2_interp_mlp_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "b200pn2_mlp_plan_bytes": (c_size_t, [c_int, c_int, c_int, ctypes.POINTER(MlpLayer), c_int, c_int]),
+    "b200pn2_mlp_plan_build": (c_int, [c_int, c_int, c_int, ctypes.POINTER(MlpLayer), c_int, c_int, c_void_p, c_size_t,
+                                       c_void_p]),
+    "b200pn2_sa_forward_planned": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_interp_mlp_forward_planned": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_void_p,
+                                                   c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_fp_rows_forward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        ctypes.POINTER(MlpLayer), c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "b200pn2_row_mlp_forward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_int,
+                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_transpose_cn": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "b200pn2_sa_tensor_work": (c_int, [ctypes.POINTER(ctypes.c_ulonglong), c_int]),
     "b200iou_boxes_overlap_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200iou_boxes_iou_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200iou_boxes_iou3d": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -85,6 +101,13 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().b200_launch_count())
+
+
+def sa_tensor_work(reset=True):
+    """Executed TF32 FLOPs of the fused tensor-core kernels on the current device since the last reset (synchronises)."""
+    n = ctypes.c_ulonglong(0)
+    check(lib().b200pn2_sa_tensor_work(ctypes.byref(n), 1 if reset else 0), "sa_tensor_work")
+    return int(n.value) * 2048
 
 
 def set_fps_policy(policy):

@@ -8,7 +8,9 @@
 //   models/ap_helper.py:187-197 / models/loss_helper_unlabeled.py:470-483 (min / max over the 8 corners).
 // The reference does this on the host in float64 numpy after a device->host copy of every head output, once per scene
 // and per box in Python.  Here one CTA handles one scene: scores are ranked, the K x K "would suppress" relation is
-// evaluated once into a bit matrix (float64, same operation order as numpy -> identical decisions), and a single warp
+// evaluated once into a bit matrix (float64, same operation order as numpy -> identical overlap decisions; boxes with
+// EQUAL scores are ordered by index, one of the orders numpy's default non-stable argsort may produce -- pick lists are
+// guaranteed identical to the reference only for distinct scores, see tests/test_oracle_aabb_nms.py), and a single warp
 // sweeps it in score order.  No host synchronisation; the pick list comes back in the reference's order.
 #include <math.h>
 

@@ -19,7 +19,8 @@ constexpr int BQ_TILE = 1024;  // points per shared-memory tile (12 KB)
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(int N, int M, float radius2, int nsample, const float *__restrict__ new_xyz,
-                  const float *__restrict__ xyz, int32_t *__restrict__ idx) {
+                  const float *__restrict__ xyz, int32_t *__restrict__ idx, int *__restrict__ unit_list,
+                  int *__restrict__ unit_total) {
   __shared__ float s_pts[BQ_TILE * 3];
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,6 +87,13 @@ ball_query_kernel(int N, int M, float radius2, int nsample, const float *__restr
     if (c < M) {
       const int have = min(cnt[q], nsample);
       for (int l = have + lane; l < nsample; l += 32) idx[((size_t)b * M + c) * nsample + l] = first[q];
+      if (unit_list && lane == 0) {
+        // the fused SA kernel only feeds the 16-slot units that hold distinct neighbours through the MLP (sa_tcp.cu):
+        // slots [0, have) are distinct ascending indices, the rest copies of slot 0
+        const int units = ((max(have, 1) - 1) >> 4) + 1;
+        const int base = atomicAdd(unit_total, units);
+        for (int u = 0; u < units; ++u) unit_list[base + u] = (b * M + c) * 8 + u;
+      }
     }
   }
 }
@@ -93,21 +101,22 @@ ball_query_kernel(int N, int M, float radius2, int nsample, const float *__restr
 // ball_query_grid.cu
 bool ball_query_grid_wanted(int B, int N, int M, float radius);
 int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
-                           int32_t *idx, cudaStream_t stream);
+                           int32_t *idx, cudaStream_t stream, int *unit_list, int *unit_total);
 
-// shared with sa_fused.cu
+// shared with sa_fused.cu.  unit_list / unit_total (optional, device): every centre appends the 16-slot units of its
+// neighbour list that hold distinct neighbours (compacted tiles of the fused SA kernel, sa_tcp.cu)
 int ball_query_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
-                      int32_t *idx, cudaStream_t stream) {
+                      int32_t *idx, cudaStream_t stream, int *unit_list, int *unit_total) {
   B200_CHECK_ARG(B >= 0 && N >= 0 && M >= 0 && nsample >= 0, "ball_query: bad sizes B=%d N=%d M=%d nsample=%d", B,
                  N, M, nsample);
   if (B == 0 || M == 0 || nsample == 0) return 0;
   B200_CHECK_ARG(new_xyz && xyz && idx, "ball_query: null pointer");
   B200_CHECK_ARG(B <= 65535, "ball_query: B=%d exceeds grid.y", B);
   if (ball_query_grid_wanted(B, N, M, radius))
-    return ball_query_grid_launch(B, N, M, radius, nsample, new_xyz, xyz, idx, stream);
+    return ball_query_grid_launch(B, N, M, radius, nsample, new_xyz, xyz, idx, stream, unit_list, unit_total);
   const float radius2 = radius * radius;  // ball_query_gpu.cu:27, one fp32 multiply
   dim3 grid(ceil_div(M, BQ_WARPS * BQ_QW), B);
-  ball_query_kernel<<<grid, BQ_WARPS * 32, 0, stream>>>(N, M, radius2, nsample, new_xyz, xyz, idx);
+  ball_query_kernel<<<grid, BQ_WARPS * 32, 0, stream>>>(N, M, radius2, nsample, new_xyz, xyz, idx, unit_list, unit_total);
   B200_LAUNCH_OK("ball_query_kernel");
   return 0;
 }
@@ -116,5 +125,5 @@ int ball_query_launch(int B, int N, int M, float radius, int nsample, const floa
 
 extern "C" int b200pn2_ball_query(int B, int N, int M, float radius, int nsample, const float *new_xyz,
                                   const float *xyz, int32_t *idx, b200_stream_t stream) {
-  return b200::ball_query_launch(B, N, M, radius, nsample, new_xyz, xyz, idx, (cudaStream_t)stream);
+  return b200::ball_query_launch(B, N, M, radius, nsample, new_xyz, xyz, idx, (cudaStream_t)stream, nullptr, nullptr);
 }

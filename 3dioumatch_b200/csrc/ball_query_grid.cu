@@ -63,7 +63,8 @@ bg_reorder_kernel(int N, int total, const float *__restrict__ xyz, const unsigne
 __global__ void __launch_bounds__(BG_WARPS * 32)
 bg_query_kernel(int N, int M, float radius2, int nsample, float inv_cell, unsigned mask, int table_bits,
                 const float *__restrict__ new_xyz, const float *__restrict__ xyz, const float4 *__restrict__ sorted_pts,
-                const int *__restrict__ start, const int *__restrict__ end, int32_t *__restrict__ idx) {
+                const int *__restrict__ start, const int *__restrict__ end, int32_t *__restrict__ idx,
+                int *__restrict__ unit_list, int *__restrict__ unit_total) {
   __shared__ int s_hits[BG_WARPS][BG_CAP];
   __shared__ int s_bs[BG_WARPS][32], s_bo[BG_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,6 +144,11 @@ bg_query_kernel(int N, int M, float radius2, int nsample, float inv_cell, unsign
       }
     }
     for (int l = min(have, nsample) + lane; l < nsample; l += 32) row[l] = first;
+    if (unit_list && lane == 0) {  // compacted tiles of the fused SA kernel (sa_tcp.cu): units holding distinct neighbours
+      const int units = ((max(min(have, nsample), 1) - 1) >> 4) + 1;
+      const int base = atomicAdd(unit_total, units);
+      for (int u = 0; u < units; ++u) unit_list[base + u] = (b * M + c) * 8 + u;
+    }
     return;
   }
 
@@ -161,6 +167,11 @@ bg_query_kernel(int N, int M, float radius2, int nsample, float inv_cell, unsign
     prev = best;
   }
   for (int l = t + lane; l < nsample; l += 32) row[l] = first;  // pad with the first hit; all zeros when empty
+  if (unit_list && lane == 0) {
+    const int units = ((max(t, 1) - 1) >> 4) + 1;  // t distinct ascending hits, then copies of the first
+    const int base = atomicAdd(unit_total, units);
+    for (int u = 0; u < units; ++u) unit_list[base + u] = (b * M + c) * 8 + u;
+  }
 }
 
 // Workspace layout (bytes): keys[2][total] u32, vals[2][total] i32, sorted_pts[total] float4, start/end[B << table_bits]
@@ -188,7 +199,7 @@ bool ball_query_grid_wanted(int B, int N, int M, float radius) {
 }
 
 int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
-                           int32_t *idx, cudaStream_t stream) {
+                           int32_t *idx, cudaStream_t stream, int *unit_list, int *unit_total) {
   int table_bits = 1;
   while ((1 << table_bits) < 2 * N) ++table_bits;
   int bbits = 0;
@@ -201,8 +212,9 @@ int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const
 
   size_t cub_bytes = 0;
   const size_t ws_bytes = bg_workspace_bytes(B, N, table_bits, &cub_bytes);
-  char *ws = nullptr;
-  B200_CUDA_OK(scratch_alloc((void **)&ws, ws_bytes, stream));
+  ScratchGuard guard;  // returned to the pool on every exit path
+  B200_CUDA_OK(guard.alloc(ws_bytes, stream));
+  char *ws = (char *)guard.ptr;
   unsigned *keys_in = (unsigned *)ws, *keys_out = keys_in + total;
   int *vals_in = (int *)(keys_out + total), *vals_out = vals_in + total;
   float4 *sorted_pts = (float4 *)(vals_out + total);  // 16-byte aligned: 4 * total * 4 bytes precede it
@@ -221,9 +233,8 @@ int ball_query_grid_launch(int B, int N, int M, float radius, int nsample, const
   B200_LAUNCH_OK("bg_reorder_kernel");
   dim3 grid(ceil_div(M, BG_WARPS), B);
   bg_query_kernel<<<grid, BG_WARPS * 32, 0, stream>>>(N, M, radius2, nsample, inv_cell, mask, table_bits, new_xyz, xyz,
-                                                      sorted_pts, start, end, idx);
+                                                      sorted_pts, start, end, idx, unit_list, unit_total);
   B200_LAUNCH_OK("bg_query_kernel");
-  B200_CUDA_OK(cudaFreeAsync(ws, stream));
   return 0;
 }
 

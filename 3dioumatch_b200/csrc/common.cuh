@@ -40,16 +40,44 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
     b200::count_launch();                                                                      \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Per-device host caches.  The library is called from one python thread per replica under nn.DataParallel
+// (train.py:187-191 of the reference), each bound to its own device: nothing below may be a process-global scalar.
+constexpr int B200_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < B200_MAX_DEVICES) ? dev : 0;
 }
+
+inline int num_sms() {
+  static std::atomic<int> n[B200_MAX_DEVICES] = {};
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is kept by the runtime PER DEVICE: remember the largest opt-in made for a
+// kernel on each device (one DynSmemOptIn object per kernel instantiation, usually a function-local static).
+struct DynSmemOptIn {
+  std::atomic<size_t> bytes[B200_MAX_DEVICES] = {};
+  template <typename Kernel>
+  cudaError_t ensure(Kernel kern, size_t need) {
+    const int dev = current_device();
+    if (need <= bytes[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e == cudaSuccess) {  // racing threads of one device may both set it: the attribute only ever grows
+      size_t cur = bytes[dev].load(std::memory_order_relaxed);
+      while (cur < need && !bytes[dev].compare_exchange_weak(cur, need, std::memory_order_release)) {
+      }
+    }
+    return e;
+  }
+};
 
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -57,20 +85,35 @@ __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1
 // synchronisation unless a release threshold is set, which turns each eager call after a sync into a driver
 // allocation (hundreds of microseconds); keep them pooled instead.
 inline cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t stream) {
-  static bool tuned[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !tuned[dev]) {
+  static std::atomic<bool> tuned[B200_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!tuned[dev].load(std::memory_order_relaxed)) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaGetLastError();
-    tuned[dev] = true;
+    tuned[dev].store(true, std::memory_order_relaxed);
   }
   return cudaMallocAsync(p, bytes, stream);
 }
+
+// Stream-ordered scratch that is returned to the pool on every exit path of a launcher (error returns included).
+struct ScratchGuard {
+  void *ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  ScratchGuard() = default;
+  ScratchGuard(const ScratchGuard &) = delete;
+  ScratchGuard &operator=(const ScratchGuard &) = delete;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    return scratch_alloc(&ptr, bytes, s);
+  }
+  ~ScratchGuard() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+};
 
 // ---- the reference's squared-distance rounding sequence -------------------------------------
 // nvcc contracts (a*a + b*b + c*c) of the reference kernels (ball_query_gpu.cu:36-37,

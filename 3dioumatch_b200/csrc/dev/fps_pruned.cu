@@ -16,8 +16,8 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "../../include/b200_pointnet2.h"
-#include "common.cuh"
+#include "../../../include/b200_pointnet2.h"
+#include "../common.cuh"
 
 namespace cg = cooperative_groups;
 

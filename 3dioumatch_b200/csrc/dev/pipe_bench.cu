@@ -3,7 +3,7 @@
 // and the question is which pipe (FMA: FFMA / FFMA2 / FADD2, ALU: FMNMX / FSETP+FSEL / SEL) sets that.
 // One CTA on one SM; every warp runs `iters` rounds of 64 independent-chain instructions of one kind (8 chains x 8);
 // result = SM cycles per warp-instruction per scheduler  ( = elapsed * 4 / (warps * instructions) ).
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace b200 {
 

@@ -9,8 +9,8 @@
 //   b200_debug_tc_gemm_ts : C[128 x N] = A[128 x K] * W[N x K]^T with the A operand staged in TENSOR MEMORY
 //                        (tcgen05.st) and split-precision TF32, pinning the TMEM A-operand layout before the fused
 //                        kernel relies on it.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../tc_common.cuh"
 
 namespace b200 {
 

@@ -1,8 +1,8 @@
 // tc_gemm_test.cu -- developer self-test of the tcgen05 building blocks (tc_common.cuh): C[128 x N] = A[128 x K] * W[N x K]^T
 // with split-precision TF32 (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM).  Not part of the public ABI; used by
 // tests/test_gpu_tc_gemm.py to pin descriptor encodings / swizzle / TMEM addressing before the fused kernel relies on them.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../tc_common.cuh"
 
 namespace b200 {
 

@@ -361,9 +361,11 @@ fps_global_kernel(int N, int m, int L, const float *__restrict__ xyz, float *__r
   }
 }
 
-// fps_pruned.cu: Morton-ordered clusters with exact spatial pruning (large clouds)
+#ifdef B200_DEV
+// dev/fps_pruned.cu (developer library only): Morton-ordered clusters with exact spatial pruning -- a measured dead end
 bool fps_pruned_wanted(int B, int N, int m);
 int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx, cudaStream_t stream);
+#endif
 
 // ---- host side -----------------------------------------------------------------------------------
 typedef void (*fps_fn)(int, int, int, int, const float *, int32_t *);
@@ -469,10 +471,12 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   int L = 0;
   while ((1 << L) < bs) ++L;
 
+#ifdef B200_DEV
   if (fps_pruned_wanted(B, N, m)) {
     const int rc = fps_pruned_launch(B, N, m, L, xyz, idx, stream);
     if (rc >= 0) return rc;  // -1: shape not handled there
   }
+#endif
   // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
   // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
   // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.

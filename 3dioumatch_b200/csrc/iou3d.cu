@@ -433,11 +433,8 @@ extern "C" int b200iou_nms_device(int n, const float *boxes, float thresh, int m
   B200_LAUNCH_OK("nms_mask_kernel");
   const size_t smem = sizeof(unsigned long long) * (size_t)col_blocks;
   if (smem > 48 * 1024) {
-    static size_t set = 0;
-    if (smem > set) {
-      B200_CUDA_OK(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set = smem;
-    }
+    static DynSmemOptIn optin;
+    B200_CUDA_OK(optin.ensure(nms_sweep_kernel, smem));
   }
   const int threads = col_blocks <= 64 ? 64 : (col_blocks <= 256 ? 256 : 1024);
   nms_sweep_kernel<<<1, threads, smem, st>>>(n, col_blocks, workspace, keep_dev, num_dev);
@@ -451,18 +448,22 @@ extern "C" int b200iou_nms(int n, const float *boxes, float thresh, int mode, in
   B200_CHECK_ARG(n >= 0 && num_out && (keep_host || n == 0), "nms: bad arguments");
   *num_out = 0;
   if (n == 0) return 0;
-  // cached device workspace + pinned staging (the reference cudaMalloc/cudaFree's per call, iou3d_nms.cpp:102-114)
-  static unsigned long long *d_ws = nullptr;
-  static int32_t *d_keep = nullptr, *h_pinned = nullptr;
-  static size_t cap_n = 0;
+  // stream-ordered device workspace + a per-call pinned staging buffer owned by the caller's thread: no state shared
+  // between devices or threads (the reference cudaMalloc/cudaFree's per call, iou3d_nms.cpp:102-114)
+  const size_t cb = ((size_t)n + 63) / 64;
+  const size_t ws_bytes = (sizeof(unsigned long long) * (size_t)n * cb + 255) & ~(size_t)255;
+  ScratchGuard ws;
+  B200_CUDA_OK(ws.alloc(ws_bytes + sizeof(int32_t) * ((size_t)n + 1), st));
+  unsigned long long *d_ws = (unsigned long long *)ws.ptr;
+  int32_t *d_keep = (int32_t *)((char *)ws.ptr + ws_bytes);
+  thread_local int32_t *h_pinned = nullptr;  // pinned host memory is not tied to a device
+  thread_local size_t cap_n = 0;
   if ((size_t)n > cap_n) {
-    if (d_ws) { cudaFree(d_ws); cudaFree(d_keep); cudaFreeHost(h_pinned); d_ws = nullptr; }
-    const size_t cn = (size_t)n + 1024;
-    const size_t cb = (cn + 63) / 64;
-    B200_CUDA_OK(cudaMalloc(&d_ws, sizeof(unsigned long long) * cn * cb));
-    B200_CUDA_OK(cudaMalloc(&d_keep, sizeof(int32_t) * (cn + 1)));
-    B200_CUDA_OK(cudaMallocHost(&h_pinned, sizeof(int32_t) * (cn + 1)));
-    cap_n = cn;
+    if (h_pinned) cudaFreeHost(h_pinned);
+    h_pinned = nullptr;
+    cap_n = 0;
+    B200_CUDA_OK(cudaMallocHost(&h_pinned, sizeof(int32_t) * ((size_t)n + 1025)));
+    cap_n = (size_t)n + 1024;
   }
   const int rc = b200iou_nms_device(n, boxes, thresh, mode, d_ws, d_keep + 1, d_keep, s);
   if (rc) return rc;

@@ -18,6 +18,7 @@
 
 #include "../../include/b200_pointnet2.h"
 #include "common.cuh"
+#include "sa_tc.cuh"
 
 namespace b200 {
 
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(SA_THREADS, 1) sa_mlp_max_kernel(const SaParam
 }
 
 // (B,C,N) -> (B,N,C) so that one grouped row is one contiguous, 16-byte aligned run
-__global__ void __launch_bounds__(256) transpose_cn_kernel(int C, int N, const float *__restrict__ in,
+// (B,C,N) -> (B,N,ld) with ld >= C; the padding columns [C, ld) are zero-filled
+__global__ void __launch_bounds__(256) transpose_cn_kernel(int C, int N, int ld, const float *__restrict__ in,
                                                            float *__restrict__ out) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -323,19 +325,12 @@ __global__ void __launch_bounds__(256) transpose_cn_kernel(int C, int N, const f
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int n = n0 + i, c = c0 + tx;
-    if (n < N && c < C) out[((size_t)b * N + n) * C + c] = tile[tx][i];
+    if (n < N && c < ld) out[((size_t)b * N + n) * ld + c] = c < C ? tile[tx][i] : 0.f;
   }
 }
 
 int ball_query_launch(int B, int N, int M, float radius, int nsample, const float *new_xyz, const float *xyz,
-                      int32_t *idx, cudaStream_t stream);
-// sa_tc.cu: the tcgen05 (tensor-core) version of the gather -> MLP -> max stage
-bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm);
-int sa_tc_launch(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz, const float *xyz,
-                 const float *feat_pm, const float *new_xyz, const int32_t *idx, int num_layers,
-                 const b200_mlp_layer *layers, float *out, float *out_pm, cudaStream_t stream,
-                 const int32_t *idx3 = nullptr, const float *w3 = nullptr, const float *rel3 = nullptr);
-
+                      int32_t *idx, cudaStream_t stream, int *unit_list, int *unit_total);
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace b200
@@ -345,10 +340,24 @@ using namespace b200;
 // Feature-propagation rows through the same fused MLP + max kernel: row (centre g, sample s) =
 // [rel_xyz (3) | sum_t weight_t * known_feats[idx_t] (C)]  (models/grid_conv_module.py:87-113 of the reference:
 // three_nn -> inverse-distance weights -> gather/blend -> cat(relative grid) -> SharedMLP -> max over the 64 grid points)
-extern "C" int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample, int C, const float *known_feats,
-                                          const float *known_feats_pm, const int32_t *idx3, const float *weight3,
-                                          const float *rel_xyz, int num_layers, const b200_mlp_layer *layers,
-                                          float *out, void *workspace, size_t workspace_bytes, b200_stream_t stream_) {
+extern "C" int b200pn2_transpose_cn(int B, int C, int N, const float *in_cm, float *out_pm, int out_ld,
+                                    b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(B >= 0 && C > 0 && N > 0 && in_cm && out_pm && (out_ld == 0 || out_ld >= C), "transpose_cn: bad arguments");
+  B200_CHECK_ARG(B <= 65535, "transpose_cn: B=%d exceeds grid.z", B);
+  if (B == 0) return 0;
+  const int ld = out_ld > 0 ? out_ld : C;
+  dim3 grid(ceil_div(N, 32), ceil_div(ld, 32), B);
+  transpose_cn_kernel<<<grid, 256, 0, stream>>>(C, N, ld, in_cm, out_pm);
+  B200_LAUNCH_OK("transpose_cn_kernel");
+  return 0;
+}
+
+extern "C" int b200pn2_interp_mlp_forward_planned(int B, int m_known, int M, int nsample, int C, const float *known_feats,
+                                                  const float *known_feats_pm, const int32_t *idx3, const float *weight3,
+                                                  const float *rel_xyz, int num_layers, const b200_mlp_layer *layers,
+                                                  float *out, void *workspace, size_t workspace_bytes, const void *plan,
+                                                  size_t plan_bytes, b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(B >= 0 && m_known > 0 && M >= 0 && C > 0 && (C & 3) == 0, "interp_mlp_forward: bad sizes");
   B200_CHECK_ARG(idx3 && weight3 && out && layers && (known_feats || known_feats_pm), "interp_mlp_forward: null pointer");
@@ -360,16 +369,68 @@ extern "C" int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample
     const size_t need = align256(sizeof(float) * (size_t)B * m_known * C);
     B200_CHECK_ARG(workspace && need <= workspace_bytes, "interp_mlp_forward: workspace too small");
     float *t = (float *)workspace;
-    dim3 grid(ceil_div(m_known, 32), ceil_div(C, 32), B);
-    transpose_cn_kernel<<<grid, 256, 0, stream>>>(C, m_known, known_feats, t);
-    B200_LAUNCH_OK("transpose_cn_kernel");
+    const int rc = b200pn2_transpose_cn(B, C, m_known, known_feats, t, 0, stream_);
+    if (rc) return rc;
     fpm = t;
   }
   B200_CHECK_ARG((((uintptr_t)fpm) & 15) == 0, "interp_mlp_forward: point-major features must be 16-byte aligned");
   B200_CHECK_ARG(sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm),
                  "interp_mlp_forward: layer widths / nsample not supported by the tensor-core kernel");
-  return sa_tc_launch(B, m_known, M, C, 1.0f, nsample, use_xyz, 0, nullptr, fpm, nullptr, nullptr, num_layers, layers, out,
-                      nullptr, stream, idx3, weight3, rel_xyz);
+  TcCall c;
+  c.mode = 1; c.B = B; c.N = m_known; c.M = M; c.C = C; c.ns = nsample; c.use_xyz = use_xyz;
+  c.feat_pm = fpm; c.idx3 = idx3; c.w3 = weight3; c.rel3 = rel_xyz; c.out = out;
+  c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
+  return sa_tc_run(c, stream);
+}
+
+extern "C" int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample, int C, const float *known_feats,
+                                          const float *known_feats_pm, const int32_t *idx3, const float *weight3,
+                                          const float *rel_xyz, int num_layers, const b200_mlp_layer *layers,
+                                          float *out, void *workspace, size_t workspace_bytes, b200_stream_t stream_) {
+  return b200pn2_interp_mlp_forward_planned(B, m_known, M, nsample, C, known_feats, known_feats_pm, idx3, weight3, rel_xyz,
+                                            num_layers, layers, out, workspace, workspace_bytes, nullptr, 0, stream_);
+}
+
+// Feature propagation rows (pointnet2_modules.py:399-420): row q of scene b = [sum_t weight3[q,t] * known[idx3[q,t]] (C2) |
+// skip[q] (C1)] -> SharedMLP stack -> one output row per q (ReLU after every layer; `relu_last` for the final one).
+extern "C" int b200pn2_fp_rows_forward(int B, int n, int m_known, int C2, int C1, const float *known_feats_pm,
+                                       const float *skip_feats_pm, const int32_t *idx3, const float *weight3,
+                                       int num_layers, const b200_mlp_layer *layers, int relu_last, float *out,
+                                       float *out_pm, const void *plan, size_t plan_bytes, b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(B >= 0 && n >= 0 && m_known > 0 && C2 > 0 && (C2 & 3) == 0 && C1 >= 0 && (C1 & 3) == 0,
+                 "fp_rows_forward: bad sizes (C2 and C1 must be multiples of 4)");
+  B200_CHECK_ARG(known_feats_pm && idx3 && weight3 && layers && (out || out_pm) && (C1 == 0 || skip_feats_pm),
+                 "fp_rows_forward: null pointer");
+  B200_CHECK_ARG(((((uintptr_t)known_feats_pm) | ((uintptr_t)skip_feats_pm)) & 15) == 0,
+                 "fp_rows_forward: point-major features must be 16-byte aligned");
+  B200_CHECK_ARG(num_layers >= 1 && layers[0].cin == C2 + C1, "fp_rows_forward: layer 0 expects cin=%d", C2 + C1);
+  if (B == 0 || n == 0) return 0;
+  TcCall c;
+  c.mode = 1; c.B = B; c.N = m_known; c.M = n; c.C = C2; c.ns = 1; c.use_xyz = 0;
+  c.feat_pm = known_feats_pm; c.idx3 = idx3; c.w3 = weight3; c.feat2_pm = skip_feats_pm; c.C2 = C1;
+  c.rowout = 1; c.final_relu = relu_last ? 1 : 0; c.rows_total = B * n; c.rows_per_scene = n;
+  c.out = out; c.out_pm = out_pm; c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
+  return sa_tc_run(c, stream);
+}
+
+// Row MLP: S scenes x R rows of C channels (point-major) -> SharedMLP stack -> rows; the 1x1-conv blocks outside the SA
+// layers (FP layers 2.., voting_module.py:38-65, proposal_module.py:98-123, grid_conv_module.py:108-115).
+extern "C" int b200pn2_row_mlp_forward(int S, int R, int C, int ld, const float *x_pm, int num_layers,
+                                       const b200_mlp_layer *layers, int relu_last, float *out, float *out_pm,
+                                       const void *plan, size_t plan_bytes, b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(S >= 0 && R >= 0 && C > 0 && (ld == 0 || ld >= C), "row_mlp_forward: bad sizes");
+  B200_CHECK_ARG(x_pm && layers && (out || out_pm), "row_mlp_forward: null pointer");
+  B200_CHECK_ARG((long long)S * R < (1ll << 30), "row_mlp_forward: too many rows");
+  B200_CHECK_ARG(num_layers >= 1 && layers[0].cin == C, "row_mlp_forward: layer 0 expects cin=%d", C);
+  if (S == 0 || R == 0) return 0;
+  TcCall c;
+  c.mode = 2; c.B = 1; c.N = S * R; c.M = S * R; c.C = C; c.ns = 32; c.use_xyz = 0;
+  c.feat_pm = x_pm; c.ld = ld;
+  c.rowout = 1; c.final_relu = relu_last ? 1 : 0; c.rows_total = S * R; c.rows_per_scene = R;
+  c.out = out; c.out_pm = out_pm; c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
+  return sa_tc_run(c, stream);
 }
 
 extern "C" size_t b200pn2_sa_forward_workspace(int B, int N, int M, int C, int nsample, int have_features_pm,
@@ -385,6 +446,17 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
                                   const float *features_pm, const float *new_xyz, const int32_t *idx_in,
                                   int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
                                   int32_t *idx_out, void *workspace, size_t workspace_bytes, b200_stream_t stream_) {
+  return b200pn2_sa_forward_planned(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, features, features_pm,
+                                    new_xyz, idx_in, num_layers, layers, out, out_pm, idx_out, workspace, workspace_bytes,
+                                    nullptr, 0, stream_);
+}
+
+extern "C" int b200pn2_sa_forward_planned(int B, int N, int M, int C, float radius, int nsample, int use_xyz,
+                                          int normalize_xyz, const float *xyz, const float *features,
+                                          const float *features_pm, const float *new_xyz, const int32_t *idx_in,
+                                          int num_layers, const b200_mlp_layer *layers, float *out, float *out_pm,
+                                          int32_t *idx_out, void *workspace, size_t workspace_bytes, const void *plan,
+                                          size_t plan_bytes, b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B200_CHECK_ARG(B >= 0 && N > 0 && M >= 0 && C >= 0, "sa_forward: bad sizes B=%d N=%d M=%d C=%d", B, N, M, C);
   B200_CHECK_ARG(num_layers >= 1 && num_layers <= SA_MAXL, "sa_forward: 1..%d layers supported, got %d", SA_MAXL,
@@ -406,38 +478,62 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
   // ---- workspace carving -----------------------------------------------------------------------------
   char *ws = (char *)workspace;
   size_t off = 0;
-  const int32_t *idx = idx_in;
-  if (!idx) {
-    int32_t *idx_buf = idx_out;
+  // point-major features first: whether the tensor-core kernel (and its compacted tiles) will run decides what the ball
+  // query has to produce
+  const float *fpm = features_pm;
+  if (C == 1 && !fpm) fpm = features;  // (B,1,N) and (B,N,1) are the same memory
+  int32_t *idx_buf = nullptr;
+  if (!idx_in) {
+    idx_buf = idx_out;
     if (!idx_buf) {
       const size_t need = align256(sizeof(int32_t) * (size_t)B * M * nsample);
       B200_CHECK_ARG(ws && off + need <= workspace_bytes, "sa_forward: workspace too small (idx)");
       idx_buf = (int32_t *)(ws + off);
       off += need;
     }
-    const int rc = ball_query_launch(B, N, M, radius, nsample, new_xyz, xyz, idx_buf, stream);
-    if (rc) return rc;
-    idx = idx_buf;
-  } else if (idx_out && idx_out != idx_in) {
-    B200_CUDA_OK(cudaMemcpyAsync(idx_out, idx_in, sizeof(int32_t) * (size_t)B * M * nsample,
-                                 cudaMemcpyDeviceToDevice, stream));
   }
-  const float *fpm = features_pm;
-  if (C == 1 && !fpm) fpm = features;  // (B,1,N) and (B,N,1) are the same memory
   if (C > 1 && !fpm) {
     const size_t need = align256(sizeof(float) * (size_t)B * N * C);
     B200_CHECK_ARG(ws && off + need <= workspace_bytes, "sa_forward: workspace too small (features_pm)");
     float *t = (float *)(ws + off);
     off += need;
-    dim3 grid(ceil_div(N, 32), ceil_div(C, 32), B);
-    transpose_cn_kernel<<<grid, 256, 0, stream>>>(C, N, features, t);
-    B200_LAUNCH_OK("transpose_cn_kernel");
+    const int rc = b200pn2_transpose_cn(B, C, N, features, t, 0, stream_);
+    if (rc) return rc;
     fpm = t;
   }
+  const bool use_tc = sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm);
+  // compacted tiles (sa_tcp.cu): the unit list is appended to by the ball query itself (or by one pass over a given idx)
+  ScratchGuard unit_scratch;
+  int *unit_total = nullptr, *unit_list = nullptr;
+  if (use_tc && sa_tcp_units_wanted(0, 0, nsample, B, M)) {
+    B200_CUDA_OK(unit_scratch.alloc(256 + sa_tcp_unit_list_bytes(B, M, nsample), stream));
+    unit_total = (int *)unit_scratch.ptr;
+    unit_list = (int *)((char *)unit_scratch.ptr + 256);
+    B200_CUDA_OK(cudaMemsetAsync(unit_total, 0, sizeof(int), stream));
+  }
+  const int32_t *idx = idx_in;
+  if (!idx) {
+    const int rc = ball_query_launch(B, N, M, radius, nsample, new_xyz, xyz, idx_buf, stream, unit_list, unit_total);
+    if (rc) return rc;
+    idx = idx_buf;
+  } else {
+    if (idx_out && idx_out != idx_in)
+      B200_CUDA_OK(cudaMemcpyAsync(idx_out, idx_in, sizeof(int32_t) * (size_t)B * M * nsample, cudaMemcpyDeviceToDevice,
+                                   stream));
+    if (unit_list) {
+      const int rc = sa_tcp_units_from_idx(B, M, nsample, idx, unit_list, unit_total, stream);
+      if (rc) return rc;
+    }
+  }
   const bool vec_ok = fpm && (C & 3) == 0 && ((((uintptr_t)fpm) & 15) == 0);
-  if (sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm))
-    return sa_tc_launch(B, N, M, C, radius, nsample, use_xyz, normalize_xyz, xyz, fpm, new_xyz, idx, num_layers, layers,
-                        out, out_pm, stream);
+  if (use_tc) {
+    TcCall c;
+    c.mode = 0; c.B = B; c.N = N; c.M = M; c.C = C; c.ns = nsample; c.use_xyz = use_xyz; c.normalize_xyz = normalize_xyz;
+    c.radius = radius; c.xyz = xyz; c.feat_pm = fpm; c.new_xyz = new_xyz; c.idx = idx; c.out = out; c.out_pm = out_pm;
+    c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
+    c.unit_list = unit_list; c.unit_total = unit_total;
+    return sa_tc_run(c, stream);
+  }
 
   SaParams p;
   p.B = B; p.N = N; p.M = M; p.C = C; p.ns = nsample; p.use_xyz = use_xyz ? 1 : 0; p.nl = num_layers;
@@ -460,11 +556,8 @@ extern "C" int b200pn2_sa_forward(int B, int N, int M, int C, float radius, int 
   const size_t smem = sizeof(float) * ((size_t)SA_R * p.ldA + (size_t)SA_R * p.ldB + 2 * SA_KC * SA_WLD) +
                       sizeof(int) * ((size_t)SA_MAXG * cout_last + SA_R) + sizeof(float) * (SA_MAXG * 3 + 4);
   B200_CHECK_ARG(smem <= 227 * 1024, "sa_forward: channel widths need %zu B of shared memory (> 227 KB)", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sa_mlp_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static DynSmemOptIn optin;
+  B200_CUDA_OK(optin.ensure(sa_mlp_max_kernel, smem));
   dim3 grid(ceil_div(M, p.G), B);
   sa_mlp_max_kernel<<<grid, SA_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_mlp_max_kernel");

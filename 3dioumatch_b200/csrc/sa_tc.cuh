@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/b200_pointnet2.h"
+
 namespace b200 {
 
 constexpr int TC_ROWS = 128;
@@ -56,12 +58,46 @@ struct TcParams {
   // kernel then runs layers 2.. only.
   int pre, rowout, rows_total;
   const float *wx;
+  // row output (ROWOUT kernels): ReLU on the last layer or not; channel-major destination `out` is (S, cout,
+  // rows_per_scene) with S = rows_total / rows_per_scene; point-major destination `out_pm` is (rows_total, cout)
+  int final_relu, rows_per_scene;
+  // mode 1, optional second source: row q's own C2 features follow the C blended channels (feature propagation)
+  const float *feat2_pm;
+  int C2;
+  int ld;  // mode 2: row stride of feat_pm in floats (>= C; rows padded to a multiple of 4 floats stay vector-loadable)
   TcLayer L[TC_MAXL];
 };
 
 
-// sa_tcp.cu: launches the persistent kernel on a fully prepared parameter block (weights already packed)
-int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_t stream);
-size_t sa_tcp_unit_scratch_bytes(int B, int M, int nsample);
+// sa_tcp.cu: launches the persistent kernel on a fully prepared parameter block (weights already packed, tile counter
+// zeroed in stream order, unit list + total already built when p.units is set)
+int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream);
+// compacted-tile bookkeeping: appends the 16-slot units of every centre's neighbour list (sa_tcp.cu)
+size_t sa_tcp_unit_list_bytes(int B, int M, int nsample);
+bool sa_tcp_units_wanted(int mode, int rowout, int nsample, int B, int M);
+int sa_tcp_units_from_idx(int B, int M, int nsample, const int32_t *idx, int *unit_list, int *total, cudaStream_t stream);
+
+// sa_launch.cu: one SharedMLP stack on the tensor-core kernel, from one row source
+struct TcCall {
+  int mode = 0;  // 0 ball-query lists, 1 three-neighbour blends (+ optional skip rows), 2 plain rows
+  int B = 0, N = 0, M = 0, C = 0, ns = 1, use_xyz = 0, normalize_xyz = 0;
+  float radius = 1.f;
+  const float *xyz = nullptr, *feat_pm = nullptr, *new_xyz = nullptr;
+  const int32_t *idx = nullptr;
+  const int32_t *idx3 = nullptr;
+  const float *w3 = nullptr, *rel3 = nullptr;
+  const float *feat2_pm = nullptr;
+  int C2 = 0;
+  int ld = 0;  // mode 2: row stride (0: C)
+  int rowout = 0, final_relu = 1, rows_total = 0, rows_per_scene = 0;
+  float *out = nullptr, *out_pm = nullptr;
+  int num_layers = 0;
+  const b200_mlp_layer *layers = nullptr;
+  const void *plan = nullptr;      // packed by b200pn2_mlp_plan_build for exactly this stack, or NULL
+  size_t plan_bytes = 0;
+  int *unit_list = nullptr, *unit_total = nullptr;  // compacted tiles: built by the ball query (or sa_tcp_units_from_idx)
+};
+bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm);
+int sa_tc_run(const TcCall &c, cudaStream_t stream);
 
 }  // namespace b200

@@ -132,11 +132,13 @@ __device__ __forceinline__ void transpose_max(float (&v)[32], int lane, int top_
 // The reference's ball query pads a neighbour list shorter than nsample with copies of its first hit
 // (ball_query_gpu.cu:40-46), and max() over duplicated rows is the max over the distinct ones, so only the slots up
 // to the last one that differs from slot 0 need to go through the MLP (true for any index list, padded or not).
-// sa_unit_count_kernel: per centre the number of 16-slot units (one warp per centre); sa_unit_scan_kernel: exclusive
-// scan over all B*M centres and the unit list (unit -> centre * 8 + unit-in-centre) the persistent kernel's producers
-// walk.  total[0] = number of units.
-__global__ void __launch_bounds__(256) sa_unit_count_kernel(int centres, int ns, const int32_t *__restrict__ idx,
-                                                           int *__restrict__ units) {
+// The unit list (unit -> centre * 8 + unit-in-centre) is built by ATOMIC APPEND: the ball-query kernels append a centre's
+// units the moment its neighbour row is final (ball_query.cu, ball_query_grid.cu), sa_unit_append_kernel does the same
+// for caller-provided index lists.  The order of the list -- hence which units share a tile -- varies from run to run;
+// the results do not: every output row of the MLP depends on its own input row only, and a centre's units meet through
+// an order-independent integer max.  total[0] = number of units (zeroed in stream order by the launcher).
+__global__ void __launch_bounds__(256) sa_unit_append_kernel(int centres, int ns, const int32_t *__restrict__ idx,
+                                                            int *__restrict__ unit_list, int *__restrict__ total) {
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per centre, coalesced row
   if (c >= centres) return;
   const int32_t *row = idx + (size_t)c * ns;
@@ -147,47 +149,16 @@ __global__ void __launch_bounds__(256) sa_unit_count_kernel(int centres, int ns,
     const unsigned m = __ballot_sync(0xffffffffu, t < ns && row[t] != first);
     if (m) last_diff = t0 + 31 - __clz(m);
   }
-  if (lane == 0) units[c] = (last_diff >> 4) + 1;
+  if (lane == 0) {
+    const int units = (last_diff >> 4) + 1;
+    const int base = atomicAdd(total, units);
+    for (int u = 0; u < units; ++u) unit_list[base + u] = c * 8 + u;
+  }
 }
 
-__global__ void __launch_bounds__(1024) sa_unit_scan_kernel(int centres, const int *__restrict__ units_in,
-                                                           int *__restrict__ unit_list, int *__restrict__ total) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base, s_chunk;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int c0 = 0; c0 < centres; c0 += 1024) {
-    const int c = c0 + tid;
-    const int units = c < centres ? units_in[c] : 0;
-    int incl = units;  // inclusive scan inside the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {  // exclusive scan of the 32 warp totals
-      const int w = s_warp[lane];
-      int wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += v;
-      }
-      s_warp[lane] = wi - w;
-      if (lane == 31) s_chunk = wi;
-    }
-    __syncthreads();
-    const int base = s_base + s_warp[warp] + (incl - units);
-    for (int u = 0; u < units; ++u) unit_list[base + u] = c * 8 + u;
-    __syncthreads();
-    if (tid == 0) s_base += s_chunk;
-    __syncthreads();
-  }
-  if (tid == 0) total[0] = s_base;
-}
+// Tensor-pipe work actually issued by sa_tcp_kernel since the last read (b200pn2_sa_tensor_work): bench.py turns it into
+// executed TF32 FLOP/s for the roofline.
+__device__ unsigned long long g_sa_mma_cols;
 
 #ifdef B200_TC_PROFILE
 __device__ unsigned long long g_tcp_prof[48];
@@ -224,7 +195,10 @@ __device__ unsigned long long g_tcp_prof[48];
 // MODE: row source (0 ball-query lists, 1 three-neighbour blends, 2 plain row GEMM with row output); PRE: factorised first
 // layer (rows of P + xyz FMAs + ReLU in the producers).  Compile-time so that each variant's producer only carries its own
 // registers -- the gather is register-bound (a runtime-mode kernel with one more row source measured 20 % slower).
-template <int MODE, int PRE>
+// ROWOUT: the final epilogue stores every row's output (point-major and/or channel-major, optional ReLU) instead of the
+// max over nsample rows -- the per-point GEMM of a factorised first layer, the feature-propagation MLP and the 1x1-conv
+// heads (row MLPs).
+template <int MODE, int PRE, int ROWOUT>
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -311,8 +285,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       TPW(0, &tq_empty[slot], (uint32_t)(((n_pub / TP_TQ) & 1) ^ 1));
       int t = 0;
       if (lane == 0) {
-        if (MODE == 2 && n_pub >= 2) {
-          // single-layer row GEMM: a CTA takes at most two tiles, one per TMEM accumulator region.  A third would
+        if (nl == 1 && n_pub >= 2) {
+          // single-layer stack: a CTA takes at most two tiles, one per TMEM accumulator region.  A third would
           // reuse the first one's region, and with one layer there is no hidden hand-off that orders its MMAs after
           // that tile's epilogue (the launcher sizes the grid so that two per CTA cover every tile).
           t = -1;
@@ -350,6 +324,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   } else if (warp == TP_MMA_WARP) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
     uint32_t sw = 0, pw = 0, sa = 0, pa = 0, n_xr = 0, tl = 0;
+    unsigned long long mma_cols = 0;  // sum over issued MMAs of their N (each MMA = 128 x N x 8 TF32 multiply-adds)
     const uint32_t r1_addr = tc::smem_addr(R1), r2_addr = tc::smem_addr(R2);
     for (;;) {
       const int t = next_tile(lane == 0);
@@ -425,6 +400,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             }
             __syncwarp();
             TP_END(7);
+            mma_cols += (unsigned long long)(3 * nks) * (unsigned)p.L[l].rows;
             if (l == 0 && ++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1u; }
             sw = sw2 + 1; pw = pw2;
             if (sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
@@ -441,6 +417,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       }
       ++tl;
     }
+    if (lane == 0 && mma_cols) atomicAdd(&g_sa_mma_cols, mma_cols);
   }
   } else if (warp >= 8) {
     // ================= producers: row (tid - 256) of the tile, layer-1 A operand =================
@@ -485,7 +462,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
       }
       const float *frow = (valid && C > 0 && MODE == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
-      if (valid && MODE == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * C;
+      if (valid && MODE == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * p.ld;
+      // mode 1, second source: this row's own (skip) features follow the blended channels (PointnetFPModule's
+      // torch.cat([interpolated, unknow_feats]), pointnet2_modules.py:413-418)
+      const float *f2row = (MODE == 1 && valid && p.C2 > 0)
+                               ? p.feat2_pm + (((size_t)b * p.M + m0 + gi) * ns + slot) * p.C2 : nullptr;
       float rel[3] = {0.f, 0.f, 0.f};
       const float *f3[3] = {nullptr, nullptr, nullptr};
       float wt[3] = {0.f, 0.f, 0.f};
@@ -511,7 +492,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int ch = kb * 32 + c * 4;
-          if (valid && MODE == 1 && (PRE || ch + 3 < C)) {  // blend of the three neighbours (three_interpolate + concat)
+          if (MODE == 1 && !PRE && f2row && ch >= C) {  // skip features (C and C2 are multiples of 4 here)
+            v[c] = ch < C + p.C2 ? __ldg(reinterpret_cast<const float4 *>(f2row + (ch - C))) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (valid && MODE == 1 && (PRE || ch + 3 < C)) {  // blend of the three neighbours (three_interpolate + concat)
             const float4 a0 = __ldg(reinterpret_cast<const float4 *>(f3[0] + ch));
             const float4 a1 = __ldg(reinterpret_cast<const float4 *>(f3[1] + ch));
             const float4 a2 = __ldg(reinterpret_cast<const float4 *>(f3[2] + ch));
@@ -578,15 +561,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       };
       // register double buffer: the loads of k-block kb+1 are in flight while kb is split and stored; the operand ring
       // is private to layer 1, so the whole gather runs ahead of the MMAs (up to TP_ASTAGES k-blocks)
+      // (a single-layer stack with two output halves consumes the operand once per half: emit it twice)
       const int nkb1 = p.L[0].nkb;
-      float4 va[8], vb[8];
-      load_kb(0, va);
-      for (int kb = 0; kb < nkb1; kb += 2) {
-        if (kb + 1 < nkb1) load_kb(kb + 1, vb);
-        store_kb(kb, va);
-        if (kb + 1 < nkb1) {
-          if (kb + 2 < nkb1) load_kb(kb + 2, va);
-          store_kb(kb + 1, vb);
+      const int reps = nl == 1 ? p.L[0].nhalf : 1;
+      for (int rep = 0; rep < reps; ++rep) {
+        float4 va[8], vb[8];
+        load_kb(0, va);
+        for (int kb = 0; kb < nkb1; kb += 2) {
+          if (kb + 1 < nkb1) load_kb(kb + 1, vb);
+          store_kb(kb, va);
+          if (kb + 1 < nkb1) {
+            if (kb + 2 < nkb1) load_kb(kb + 2, va);
+            store_kb(kb + 1, vb);
+          }
         }
       }
     }
@@ -686,21 +673,52 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                 v[c * 4 + 2] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z), 0.f);
                 v[c * 4 + 3] = fmaxf(fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w), 0.f);
               }
-              if ((MODE == 2)) {
-                // plain row GEMM: affine without the ReLU, this row's 32 columns stored as one 128-byte run
-                const size_t grow = (size_t)t * TC_ROWS + row;
-                if (grow < (size_t)p.rows_total) {
-                  float4 *dst = reinterpret_cast<float4 *>(p.out_pm + grow * cout + c0);
+              if (ROWOUT) {
+                // row output: affine (+ ReLU when asked), this row's 32 columns.  Point-major: one 128-byte run per row
+                // (width a multiple of 4); channel-major (B, cout, rows_per_scene): lanes = consecutive rows, coalesced
+                // per column.  Columns past cout (stacks padded to a multiple of 32) are dropped.
+                size_t grow;
+                bool rvalid;
+                if (MODE == 2) {
+                  grow = (size_t)t * TC_ROWS + row;
+                  rvalid = grow < (size_t)p.rows_total;
+                } else {
+                  const int gg = row / ns;
+                  rvalid = gg < g_here;
+                  grow = ((size_t)b * p.M + m0 + gg) * ns + (row - gg * ns);
+                }
+                if (rvalid) {
+                  float o[32];
 #pragma unroll
                   for (int c = 0; c < 8; ++c) {
                     const float4 s4 = *reinterpret_cast<const float4 *>(sc + c0 + c * 4);
                     const float4 h4 = *reinterpret_cast<const float4 *>(sh + c0 + c * 4);
-                    float4 o;
-                    o.x = fmaf(__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]), s4.x, h4.x);
-                    o.y = fmaf(__uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]), s4.y, h4.y);
-                    o.z = fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z);
-                    o.w = fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w);
-                    dst[c] = o;
+                    o[c * 4 + 0] = fmaf(__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]), s4.x, h4.x);
+                    o[c * 4 + 1] = fmaf(__uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]), s4.y, h4.y);
+                    o[c * 4 + 2] = fmaf(__uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]), s4.z, h4.z);
+                    o[c * 4 + 3] = fmaf(__uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3]), s4.w, h4.w);
+                  }
+                  if (p.final_relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+                  }
+                  if (p.out_pm) {
+                    if (c0 + 32 <= cout && (cout & 3) == 0) {
+                      float4 *dst = reinterpret_cast<float4 *>(p.out_pm + grow * cout + c0);
+#pragma unroll
+                      for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 32; ++i)
+                        if (c0 + i < cout) p.out_pm[grow * cout + c0 + i] = o[i];
+                    }
+                  }
+                  if (p.out) {
+                    const size_t sb = grow / (size_t)p.rows_per_scene, si = grow - sb * (size_t)p.rows_per_scene;
+                    float *dst = p.out + (sb * cout + c0) * (size_t)p.rows_per_scene + si;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                      if (c0 + i < cout) dst[(size_t)i * p.rows_per_scene] = o[i];
                   }
                 }
                 TP_LAP(18);
@@ -754,7 +772,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
               TP_LAP(18);
             }
           }
-          if (ns > 32 && !p.units && !(MODE == 2)) {
+          if (ns > 32 && !p.units && !ROWOUT) {
             TP_BEGIN();
             // a centre spans nsample / 32 warps: combine their maxima (double-buffered by tile, one barrier per tile)
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -803,33 +821,43 @@ extern "C" int b200_debug_tcp_profile(unsigned long long *out32) {
 }
 #endif
 
-// Geometry + launch.  `p` carries the layer table, packed weights and row sources prepared by sa_tc_launch (sa_tc.cu).
-size_t sa_tcp_unit_scratch_bytes(int B, int M, int nsample) {
-  return ((size_t)B * M * (size_t)(nsample / 16 + 2) + 64) * sizeof(int);
+// Geometry + launch.  `p` carries the layer table, packed weights and row sources prepared by sa_launch.cu.
+size_t sa_tcp_unit_list_bytes(int B, int M, int nsample) {
+  return ((size_t)B * M * (size_t)(nsample / 16 + 1) + 64) * sizeof(int);
 }
 
-int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_t stream) {
-  static int force_slots = -1, compact_rows = -1;
+// compacted tiles: neighbour lists, nsample 32..128 in whole 16-slot units (<= 8 units per centre), max-pooled output
+bool sa_tcp_units_wanted(int mode, int rowout, int nsample, int B, int M) {
+  const char *e = getenv("B200_SA_TC_UNITS");  // read per call: the parity suite runs both ways in one process
+  if (e && atoi(e) == 0) return false;
+  return mode == 0 && !rowout && nsample >= 32 && (nsample & 15) == 0 && nsample <= 128 && (long long)B * M < (1ll << 27);
+}
+
+int sa_tcp_units_from_idx(int B, int M, int nsample, const int32_t *idx, int *unit_list, int *total, cudaStream_t stream) {
+  const int centres = B * M;
+  sa_unit_append_kernel<<<ceil_div(centres, 8), 256, 0, stream>>>(centres, nsample, idx, unit_list, total);
+  B200_LAUNCH_OK("sa_unit_append_kernel");
+  return 0;
+}
+
+template <int MODE, int PRE, int ROWOUT>
+static int launch_variant(const TcParams &p, int grid, size_t smem, cudaStream_t stream) {
+  static DynSmemOptIn optin;  // one per kernel instantiation, per device inside
+  B200_CUDA_OK(optin.ensure(sa_tcp_kernel<MODE, PRE, ROWOUT>, smem));
+  sa_tcp_kernel<MODE, PRE, ROWOUT><<<grid, TP_THREADS, smem, stream>>>(p);
+  B200_LAUNCH_OK("sa_tcp_kernel");
+  return 0;
+}
+
+int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
+  static int force_slots = -1, force_astages = -1;
   if (force_slots < 0) {
     const char *e = getenv("B200_SA_TC_SLOTS");
     force_slots = e ? atoi(e) : 0;
-    e = getenv("B200_SA_TC_UNITS");
-    compact_rows = (e && atoi(e) == 0) ? 0 : 1;
+    e = getenv("B200_SA_TC_ASTAGES");
+    force_astages = e ? atoi(e) : 0;
   }
-  // compacted tiles: neighbour lists from a ball query, nsample 32..128 in whole 16-slot units, <= 8 units per centre
-  p.units = (compact_rows && unit_scratch && p.mode == 0 && p.ns >= 32 && (p.ns & 15) == 0 && p.ns <= 128 &&
-             (long long)p.B * p.M < (1ll << 27)) ? 1 : 0;
-  p.unit_list = nullptr;
-  p.total_units = nullptr;
-  if (p.units) {
-    const int centres = p.B * p.M;
-    int *units = unit_scratch + 64, *list = units + centres;  // [total | per-centre unit counts | unit list]
-    p.total_units = unit_scratch;
-    p.unit_list = list;
-    sa_unit_count_kernel<<<ceil_div(centres, 8), 256, 0, stream>>>(centres, p.ns, p.idx, units);
-    B200_LAUNCH_OK("sa_unit_count_kernel");
-    sa_unit_scan_kernel<<<1, 1024, 0, stream>>>(centres, units, list, unit_scratch);
-    B200_LAUNCH_OK("sa_unit_scan_kernel");
+  if (p.units) {  // a centre's units meet through atomicMax on zero-initialised outputs
     const int cout = p.L[p.nl - 1].cout;
     B200_CUDA_OK(cudaMemsetAsync(p.out, 0, (size_t)p.B * cout * p.M * sizeof(float), stream));
     if (p.out_pm) B200_CUDA_OK(cudaMemsetAsync(p.out_pm, 0, (size_t)p.B * cout * p.M * sizeof(float), stream));
@@ -839,11 +867,6 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float);
-  static int force_astages = -1;
-  if (force_astages < 0) {
-    const char *e = getenv("B200_SA_TC_ASTAGES");
-    force_astages = e ? atoi(e) : 0;
-  }
   p.a_stages = (force_astages >= 2 && force_astages <= TP_ASTAGES) ? force_astages : 3;
   p.r1_bytes = p.a_stages * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
@@ -853,22 +876,33 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, int *unit_scratch, cudaStream_
   if (force_slots >= 2 && force_slots < p.nslots) p.nslots = force_slots;
   B200_CHECK_ARG(p.nslots >= 2, "sa_forward(tc): weight ring does not fit (%d-byte slots)", p.wslot_bytes);
   const size_t smem = rest + (size_t)p.nslots * p.wslot_bytes;
-  void (*kern)(const TcParams) = nullptr;
-  int variant = 0;
-  if (p.mode == 2) { kern = sa_tcp_kernel<2, 0>; variant = 4; }
-  else if (p.mode == 1) { kern = p.pre ? sa_tcp_kernel<1, 1> : sa_tcp_kernel<1, 0>; variant = 2 + (p.pre ? 1 : 0); }
-  else { kern = p.pre ? sa_tcp_kernel<0, 1> : sa_tcp_kernel<0, 0>; variant = p.pre ? 1 : 0; }
-  static size_t attr[5] = {0, 0, 0, 0, 0};
-  if (smem > attr[variant]) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[variant] = smem;
-  }
-  // the tile counter was zeroed in stream order by tc_pack_weights_kernel (sa_tc.cu)
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (p.mode == 2 && 2 * grid < p.total_tiles) grid = ceil_div(p.total_tiles, 2);  // at most two tiles per CTA (see publish())
-  kern<<<grid, TP_THREADS, smem, stream>>>(p);
-  B200_LAUNCH_OK("sa_tcp_kernel");
-  return 0;
+  if (p.nl == 1 && 2 * grid < p.total_tiles) grid = ceil_div(p.total_tiles, 2);  // at most two tiles per CTA (see publish())
+  if (grid <= 0) return 0;
+  const int key = p.mode * 4 + (p.pre ? 2 : 0) + (p.rowout ? 1 : 0);
+  switch (key) {
+    case 0: return launch_variant<0, 0, 0>(p, grid, smem, stream);   // ball-query lists -> MLP -> max
+    case 2: return launch_variant<0, 1, 0>(p, grid, smem, stream);   //   with a factorised first layer
+    case 4: return launch_variant<1, 0, 0>(p, grid, smem, stream);   // three-neighbour blends -> MLP -> max (GridConv sampler)
+    case 6: return launch_variant<1, 1, 0>(p, grid, smem, stream);
+    case 5: return launch_variant<1, 0, 1>(p, grid, smem, stream);   // blends | skip features -> row output (feature propagation)
+    case 9: return launch_variant<2, 0, 1>(p, grid, smem, stream);   // plain rows -> row output (per-point GEMM, 1x1-conv heads)
+    default: break;
+  }
+  set_error("sa_forward(tc): no kernel variant for mode %d pre %d rowout %d", p.mode, p.pre, p.rowout);
+  return 1;
 }
 
 }  // namespace b200
+
+extern "C" int b200pn2_sa_tensor_work(unsigned long long *mma_n_columns, int reset) {
+  using namespace b200;
+  B200_CHECK_ARG(mma_n_columns != nullptr, "sa_tensor_work: null pointer");
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  B200_CUDA_OK(cudaMemcpyFromSymbol(mma_n_columns, g_sa_mma_cols, sizeof(unsigned long long)));
+  if (reset) {
+    const unsigned long long z = 0;
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_sa_mma_cols, &z, sizeof(z)));
+  }
+  return 0;
+}

@@ -45,22 +45,25 @@ def boxes_iou3d_batched(boxes_a, boxes_b):
     return out
 
 
-def _nms(native, boxes, scores, thresh, pre_maxsize=None):
+def _nms(normal, boxes, scores, thresh, pre_maxsize=None):
+    """Sort -> suppression mask -> greedy sweep, all on the device (b200iou_nms_device); the keep list never visits the
+    host.  The only host interaction is reading the 4-byte count, because the RESULT'S SHAPE depends on it (the reference
+    copies the whole N x N/64 mask to the host and sweeps it there, iou3d_nms.cpp:111-134)."""
     assert boxes.shape[1] == 7
     order = scores.sort(0, descending=True)[1]
     if pre_maxsize is not None:
         order = order[:pre_maxsize]
     boxes = boxes[order].contiguous()
-    keep = torch.LongTensor(boxes.size(0))
-    num_out = native(boxes, keep, thresh)
-    return order[keep[:num_out].to(boxes.device)].contiguous(), None
+    keep, num = iou3d_nms_cuda.nms_device(boxes, thresh, normal=normal)
+    num_out = int(num.item())
+    return order[keep[:num_out].long()].contiguous(), None
 
 
 def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
     """boxes (N,7), scores (N) -> (kept indices (LongTensor, CUDA), None); 3D-IoU criterion."""
-    return _nms(iou3d_nms_cuda.nms_gpu, boxes, scores, thresh, pre_maxsize)
+    return _nms(False, boxes, scores, thresh, pre_maxsize)
 
 
 def nms_normal_gpu(boxes, scores, thresh, **kwargs):
     """axis-aligned BEV IoU criterion."""
-    return _nms(iou3d_nms_cuda.nms_normal_gpu, boxes, scores, thresh)
+    return _nms(True, boxes, scores, thresh)

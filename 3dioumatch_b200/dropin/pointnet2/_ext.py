@@ -183,11 +183,49 @@ def group_points_grad(grad_out, idx, n):
     return out
 
 
-# ---- wide entry (no reference counterpart): fused ball-query -> group -> SharedMLP -> max -------------------
+# ---- wide entries (no reference counterpart): fused stages on the tensor-core SharedMLP kernels ----------------------
+
+def _layer_array(layers):
+    """[(weight (cout,cin), scale (cout,), shift (cout,))] -> (b200_mlp_layer[], tensors kept alive by the caller)."""
+    arr = (cabi.MlpLayer * len(layers))()
+    keep = []
+    for i, (w, sc, sh) in enumerate(layers):
+        for t, nm in ((w, "weight"), (sc, "scale"), (sh, "shift")):
+            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
+        w2 = w.reshape(w.size(0), -1)
+        keep.append(w2)
+        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
+        arr[i].weight, arr[i].scale, arr[i].shift = w2.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    return arr, keep
+
+
+def _plan_args(plan):
+    if plan is None:
+        return ctypes.c_void_p(0), 0
+    _chk(plan.is_cuda and plan.dtype == torch.uint8 and plan.is_contiguous(), "plan must be a contiguous CUDA uint8 tensor")
+    return _p(plan), plan.numel()
+
+
+def mlp_plan(layers, C_feat, use_xyz, row_output=False, plain_rows=False):
+    """Pack the weights of a SharedMLP stack once (include/b200_pointnet2.h: b200pn2_mlp_plan_build).  Returns a CUDA
+    uint8 tensor to pass as `plan=` to the fused entries, or None when the tensor-core kernel does not take the stack.
+    Valid until the weights / folded affine change."""
+    arr, keep = _layer_array(layers)
+    dev = layers[0][0].device
+    with torch.cuda.device(dev):
+        n = int(_L().b200pn2_mlp_plan_bytes(int(C_feat), int(bool(use_xyz)), len(layers), arr, int(bool(row_output)),
+                                            int(bool(plain_rows))))
+        if n == 0:
+            return None
+        plan = torch.empty((n,), dtype=torch.uint8, device=dev)
+        cabi.check(_L().b200pn2_mlp_plan_build(int(C_feat), int(bool(use_xyz)), len(layers), arr, int(bool(row_output)),
+                                               int(bool(plain_rows)), _p(plan), n, stream_ptr()), "mlp_plan_build")
+    return plan
+
 
 def sa_forward(xyz, features, new_xyz, radius, nsample, layers, use_xyz=True, normalize_xyz=False,
-               features_pm=None, idx=None, want_idx=False, want_pm=False):
-    """Fused set-abstraction forward (include/b200_pointnet2.h: b200pn2_sa_forward).
+               features_pm=None, idx=None, want_idx=False, want_pm=False, plan=None):
+    """Fused set-abstraction forward (include/b200_pointnet2.h: b200pn2_sa_forward_planned).
 
     xyz (B,N,3), features (B,C,N) or None, new_xyz (B,M,3); layers = [(weight (cout,cin), scale (cout,), shift (cout,))]
     returns (out (B,cout,M), out_pm (B,M,cout) or None, idx (B,M,nsample) or None)."""
@@ -204,47 +242,27 @@ def sa_forward(xyz, features, new_xyz, radius, nsample, layers, use_xyz=True, no
         C = features_pm.size(2)
     if idx is not None:
         _contig(idx, "idx"); _is_int(idx, "idx"); _cuda(idx, "idx")
-    arr = (cabi.MlpLayer * len(layers))()
-    keep_alive = []
-    for i, (w, sc, sh) in enumerate(layers):
-        for t, nm in ((w, "weight"), (sc, "scale"), (sh, "shift")):
-            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
-        w2 = w.reshape(w.size(0), -1)
-        keep_alive.append(w2)
-        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
-        arr[i].weight, arr[i].scale, arr[i].shift = w2.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    arr, keep_alive = _layer_array(layers)
     cout = layers[-1][0].size(0)
     dev = xyz.device
     out = torch.empty((B, cout, M), dtype=torch.float32, device=dev)
     out_pm = torch.empty((B, M, cout), dtype=torch.float32, device=dev) if want_pm else None
     idx_out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=dev) if (want_idx and idx is None) else None
+    pp, pn = _plan_args(plan)
     with torch.cuda.device(dev):
         nbytes = int(_L().b200pn2_sa_forward_workspace(B, N, M, C, int(nsample), int(features_pm is not None),
                                                        int(idx is not None or idx_out is not None)))
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes else None
-        cabi.check(_L().b200pn2_sa_forward(B, N, M, C, float(radius), int(nsample), int(bool(use_xyz)),
-                                           int(bool(normalize_xyz)), _p(xyz), _p(features), _p(features_pm),
-                                           _p(new_xyz), _p(idx), len(layers), arr, _p(out), _p(out_pm), _p(idx_out),
-                                           _p(ws), nbytes, stream_ptr()), "sa_forward")
+        cabi.check(_L().b200pn2_sa_forward_planned(B, N, M, C, float(radius), int(nsample), int(bool(use_xyz)),
+                                                   int(bool(normalize_xyz)), _p(xyz), _p(features), _p(features_pm),
+                                                   _p(new_xyz), _p(idx), len(layers), arr, _p(out), _p(out_pm),
+                                                   _p(idx_out), _p(ws), nbytes, pp, pn, stream_ptr()), "sa_forward")
     return out, out_pm, (idx if idx is not None else idx_out)
 
 
-def _layer_array(layers):
-    arr = (cabi.MlpLayer * len(layers))()
-    keep = []
-    for i, (w, sc, sh) in enumerate(layers):
-        for t, nm in ((w, "weight"), (sc, "scale"), (sh, "shift")):
-            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
-        w2 = w.reshape(w.size(0), -1)
-        keep.append(w2)
-        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
-        arr[i].weight, arr[i].scale, arr[i].shift = w2.data_ptr(), sc.data_ptr(), sh.data_ptr()
-    return arr, keep
-
-
-def interp_mlp_forward(known_feats, idx3, weight3, rel_xyz, nsample, layers, known_feats_pm=None):
+def interp_mlp_forward(known_feats, idx3, weight3, rel_xyz, nsample, layers, known_feats_pm=None, plan=None):
     """Fused 3-neighbour blend -> cat(rel xyz) -> SharedMLP -> max over nsample (include/b200_pointnet2.h:
-    b200pn2_interp_mlp_forward).  known_feats (B,C,m), idx3/weight3/rel_xyz (B, M*nsample, 3) -> (B, cout, M)."""
+    b200pn2_interp_mlp_forward_planned).  known_feats (B,C,m), idx3/weight3/rel_xyz (B, M*nsample, 3) -> (B, cout, M)."""
     for t, nm in ((idx3, "idx3"), (weight3, "weight3")):
         _contig(t, nm); _cuda(t, nm)
     _is_int(idx3, "idx3"); _is_float(weight3, "weight3")
@@ -264,8 +282,80 @@ def interp_mlp_forward(known_feats, idx3, weight3, rel_xyz, nsample, layers, kno
     out = torch.empty((B, layers[-1][0].size(0), M), dtype=torch.float32, device=dev)
     nbytes = 0 if known_feats_pm is not None else ((B * m * C * 4 + 255) // 256) * 256
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if nbytes else None
+    pp, pn = _plan_args(plan)
     with torch.cuda.device(dev):
-        cabi.check(_L().b200pn2_interp_mlp_forward(B, m, M, int(nsample), C, _p(known_feats), _p(known_feats_pm), _p(idx3),
-                                                   _p(weight3), _p(rel_xyz), len(layers), arr, _p(out), _p(ws), nbytes,
-                                                   stream_ptr()), "interp_mlp_forward")
+        cabi.check(_L().b200pn2_interp_mlp_forward_planned(B, m, M, int(nsample), C, _p(known_feats), _p(known_feats_pm),
+                                                           _p(idx3), _p(weight3), _p(rel_xyz), len(layers), arr, _p(out),
+                                                           _p(ws), nbytes, pp, pn, stream_ptr()), "interp_mlp_forward")
     return out
+
+
+def transpose_cn(x, ld=0):
+    """(B,C,N) channel-major -> (B,N,ld or C) point-major, zero-padded columns (b200pn2_transpose_cn)."""
+    _contig(x, "x"); _is_float(x, "x"); _cuda(x, None)
+    B, C, N = x.shape
+    width = int(ld) if ld else C
+    out = torch.empty((B, N, width), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            cabi.check(_L().b200pn2_transpose_cn(B, C, N, _p(x), _p(out), width, stream_ptr()), "transpose_cn")
+    return out
+
+
+def fp_rows_forward(known_feats_pm, skip_feats_pm, idx3, weight3, layers, relu_last=True, want_cm=True, want_pm=False,
+                    plan=None):
+    """Feature-propagation rows [blend of 3 known rows | skip row] -> SharedMLP stack -> rows (b200pn2_fp_rows_forward).
+    known_feats_pm (B,m,C2), skip_feats_pm (B,n,C1) or None, idx3/weight3 (B,n,3) -> (out (B,cout,n), out_pm (B,n,cout))."""
+    for t, nm in ((known_feats_pm, "known_feats_pm"), (idx3, "idx3"), (weight3, "weight3")):
+        _contig(t, nm); _cuda(t, nm)
+    _is_float(known_feats_pm, "known_feats_pm"); _is_int(idx3, "idx3"); _is_float(weight3, "weight3")
+    B, m, C2 = known_feats_pm.shape
+    n = idx3.size(1)
+    C1 = 0
+    if skip_feats_pm is not None:
+        _contig(skip_feats_pm, "skip_feats_pm"); _is_float(skip_feats_pm, "skip_feats_pm"); _cuda(skip_feats_pm, "skip_feats_pm")
+        C1 = skip_feats_pm.size(2)
+    arr, keep = _layer_array(layers)
+    cout = layers[-1][0].size(0)
+    dev = idx3.device
+    out = torch.empty((B, cout, n), dtype=torch.float32, device=dev) if want_cm else None
+    out_pm = torch.empty((B, n, cout), dtype=torch.float32, device=dev) if want_pm else None
+    pp, pn = _plan_args(plan)
+    with torch.cuda.device(dev):
+        cabi.check(_L().b200pn2_fp_rows_forward(B, n, m, C2, C1, _p(known_feats_pm), _p(skip_feats_pm), _p(idx3),
+                                                _p(weight3), len(layers), arr, int(bool(relu_last)), _p(out), _p(out_pm),
+                                                pp, pn, stream_ptr()), "fp_rows_forward")
+    return out, out_pm
+
+
+def row_mlp_forward(x_pm, layers, relu_last=True, want_cm=True, want_pm=False, plan=None, channels=None):
+    """1x1-conv stack on plain rows (b200pn2_row_mlp_forward).  x_pm (S,R,ld) point-major rows holding `channels` (default
+    ld) channels -> (out (S,cout,R), out_pm (S,R,cout))."""
+    _contig(x_pm, "x_pm"); _is_float(x_pm, "x_pm"); _cuda(x_pm, None)
+    S, R, ld = x_pm.shape
+    C = int(channels) if channels else ld
+    arr, keep = _layer_array(layers)
+    cout = layers[-1][0].size(0)
+    dev = x_pm.device
+    out = torch.empty((S, cout, R), dtype=torch.float32, device=dev) if want_cm else None
+    out_pm = torch.empty((S, R, cout), dtype=torch.float32, device=dev) if want_pm else None
+    pp, pn = _plan_args(plan)
+    with torch.cuda.device(dev):
+        cabi.check(_L().b200pn2_row_mlp_forward(S, R, C, ld, _p(x_pm), len(layers), arr, int(bool(relu_last)), _p(out),
+                                                _p(out_pm), pp, pn, stream_ptr()), "row_mlp_forward")
+    return out, out_pm
+
+
+def split_row_groups(layers):
+    """Cut a stack into runs one tensor-core launch can take: every layer of a run but its last is a hidden layer
+    (width a multiple of 32, <= 128), the last may be up to 256 wide; at most 4 layers per run."""
+    groups, cur = [], []
+    for w, sc, sh in layers:
+        cur.append((w, sc, sh))
+        cout = w.size(0)
+        if not (cout % 32 == 0 and cout <= 128) or len(cur) == 4:
+            groups.append(cur)
+            cur = []
+    if cur:
+        groups.append(cur)
+    return groups

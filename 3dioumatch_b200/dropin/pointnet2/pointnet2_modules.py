@@ -55,10 +55,12 @@ def _can_fuse(grouper, mlp, xyz, features, pooling="max"):
     return layers
 
 
-def _fused_stage(grouper, layers, xyz, new_xyz, features, features_pm=None, want_pm=False):
+def _fused_stage(grouper, layers, xyz, new_xyz, features, features_pm=None, want_pm=False, mlp=None):
+    C = features.size(1) if features is not None else (features_pm.size(2) if features_pm is not None else 0)
+    plan = mlp.b200_plan(layers, C, grouper.use_xyz) if (mlp is not None and hasattr(mlp, "b200_plan")) else None
     out, out_pm, _ = _ext.sa_forward(xyz, features, new_xyz, grouper.radius, grouper.nsample, layers,
                                      use_xyz=grouper.use_xyz, normalize_xyz=grouper.normalize_xyz,
-                                     features_pm=features_pm, want_pm=want_pm)
+                                     features_pm=features_pm, want_pm=want_pm, plan=plan)
     return out, out_pm
 
 
@@ -90,7 +92,7 @@ class _PointnetSAModuleBase(nn.Module):
         for grouper, mlp in zip(self.groupers, self.mlps):
             layers = _can_fuse(grouper, mlp, xyz, features) if new_xyz is not None else None
             if layers is not None:
-                outs.append(_fused_stage(grouper, layers, xyz, new_xyz, features)[0])
+                outs.append(_fused_stage(grouper, layers, xyz, new_xyz, features, mlp=mlp)[0])
             else:
                 outs.append(_pool(mlp(grouper(xyz, new_xyz, features)), "max"))
         return torch.cat(outs, dim=1)
@@ -173,7 +175,7 @@ class PointnetSAModuleVotes(nn.Module):
         if new_xyz is not None and not self.ret_unique_cnt:
             layers = _can_fuse(self.grouper, self.mlp_module, xyz, features, self.pooling)
         if layers is not None:
-            new_features, _ = _fused_stage(self.grouper, layers, xyz, new_xyz, features)
+            new_features, _ = _fused_stage(self.grouper, layers, xyz, new_xyz, features, mlp=self.mlp_module)
             return new_xyz, new_features, inds
 
         grouped = self.grouper(xyz, new_xyz, features)
@@ -217,11 +219,45 @@ class PointnetFPModule(nn.Module):
             dist, idx = pointnet2_utils.three_nn(unknown, known)
             dist_recip = 1.0 / (dist + 1e-8)
             weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+            fused = self._fused(unknown, unknow_feats, known_feats, idx, weight)
+            if fused is not None:
+                return fused
             interpolated = pointnet2_utils.three_interpolate(known_feats, idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
         new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+    def _fused(self, unknown, unknow_feats, known_feats, idx, weight):
+        """Eval mode, no gradient: blend -> concat -> SharedMLP without the interpolated / concatenated tensors ever
+        reaching HBM -- the producers of the tensor-core kernel build each row [sum_t w_t * known[idx_t] | skip] on the
+        fly (b200pn2_fp_rows_forward); layers wider than 128 chain through the row-MLP entry."""
+        if not _fused_enabled() or not known_feats.is_cuda or known_feats.dtype != torch.float32:
+            return None
+        if torch.is_grad_enabled() and (known_feats.requires_grad or (unknow_feats is not None and unknow_feats.requires_grad)
+                                        or unknown.requires_grad or any(p.requires_grad for p in self.mlp.parameters())):
+            return None
+        layers = self.mlp.fold_affine() if hasattr(self.mlp, "fold_affine") else None
+        C2 = known_feats.size(1)
+        C1 = unknow_feats.size(1) if unknow_feats is not None else 0
+        if (not layers or C2 % 4 != 0 or C1 % 4 != 0 or layers[0][0].size(1) != C1 + C2 or
+                any(w.size(0) > 256 for w, _, _ in layers)):
+            return None
+        groups = _ext.split_row_groups(layers)
+        known_pm = _ext.transpose_cn(known_feats.contiguous())
+        skip_pm = _ext.transpose_cn(unknow_feats.contiguous()) if unknow_feats is not None else None
+        out_cm = rows = None
+        chan = C1 + C2
+        for gi, grp in enumerate(groups):
+            last = gi == len(groups) - 1
+            plan = self.mlp.b200_plan(grp, chan, False, row_output=True, plain_rows=gi > 0)
+            if gi == 0:
+                out_cm, rows = _ext.fp_rows_forward(known_pm, skip_pm, idx.contiguous(), weight.contiguous(), grp,
+                                                    relu_last=True, want_cm=last, want_pm=not last, plan=plan)
+            else:
+                out_cm, rows = _ext.row_mlp_forward(rows, grp, relu_last=True, want_cm=last, want_pm=not last, plan=plan)
+            chan = grp[-1][0].size(0)
+        return out_cm
 
 
 class PointnetLFPModuleMSG(nn.Module):
@@ -239,7 +275,7 @@ class PointnetLFPModuleMSG(nn.Module):
         for grouper, mlp in zip(self.groupers, self.mlps):
             layers = _can_fuse(grouper, mlp, xyz1, features1)
             if layers is not None:
-                pooled = _fused_stage(grouper, layers, xyz1, xyz2, features1)[0]
+                pooled = _fused_stage(grouper, layers, xyz1, xyz2, features1, mlp=mlp)[0]
             else:
                 pooled = _pool(mlp(grouper(xyz1, xyz2, features1)), "max")
             if features2 is not None:

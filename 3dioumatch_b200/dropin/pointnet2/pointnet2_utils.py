@@ -216,8 +216,9 @@ def grid_interp_mlp_max(known_feats, idx, weight, rel_xyz, nsample, shared_mlp):
         layers = shared_mlp.fold_affine()
     if layers is not None and C % 4 == 0 and 128 % nsample == 0 and nsample >= 8:
         try:
+            plan = shared_mlp.b200_plan(layers, C, True) if hasattr(shared_mlp, "b200_plan") else None
             return _ext.interp_mlp_forward(known_feats.contiguous(), idx.contiguous(), weight.contiguous(),
-                                           rel_xyz.contiguous(), nsample, layers)
+                                           rel_xyz.contiguous(), nsample, layers, plan=plan)
         except RuntimeError as e:  # widths outside the tensor-core kernel's range -> generic path
             if "not supported" not in str(e):
                 raise

@@ -3,8 +3,11 @@
 reference pytorch_utils.py:14-39,42-67,70-123,226-263,265-299).
 
 Written for the fused sm_100a path: every block can export itself as an (weight, scale, shift) affine triple
-(`fold_affine`), which is what b200pn2_sa_forward consumes in eval mode.
+(`fold_affine`), which is what b200pn2_sa_forward consumes in eval mode; `freeze_inference(model)` additionally keeps
+the packed tensor-core weight images per module, and SharedMLP.forward itself runs as fused row MLPs in eval mode.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -108,19 +111,76 @@ class SharedMLP(nn.Sequential):
                             Conv2d(args[i], args[i + 1], bn=bn and not plain_first,
                                    activation=None if plain_first else activation, preact=preact))
 
-    # ---- export for the fused kernel ---------------------------------------------------------------------
+    # ---- export for the fused kernels --------------------------------------------------------------------
     def fold_affine(self):
         """[(weight (cout,cin), scale (cout,), shift (cout,))] such that each block is relu(scale*(W x)+shift),
-        or None when a block is not conv(1x1) -> [eval BN] -> ReLU.  Cached until a parameter/buffer changes
-        (tensor version counters) or the module switches between train() and eval()."""
-        stamp = tuple((id(t), t._version, t.device) for t in list(self.parameters()) + list(self.buffers())) + \
-            tuple(m.training for m in self.modules())
-        cached = getattr(self, "_b200_fold_cache", None)
-        if cached is not None and cached[0] == stamp:
-            return cached[1]
-        result = self._fold_affine_uncached()
-        object.__setattr__(self, "_b200_fold_cache", (stamp, result))
-        return result
+        or None when a block is not conv(1x1) -> [eval BN] -> ReLU.
+
+        Recomputed from the live parameters on EVERY call (a handful of tiny elementwise kernels): weights may be
+        rewritten behind autograd's back -- the reference's EMA teacher does `ema_param.data.mul_(alpha).add_(...)`
+        (train.py:285-289), which bumps no version counter -- and a captured CUDA graph must read them where they
+        live.  `b200_freeze()` trades that for zero per-call work once the weights are final."""
+        frozen = getattr(self, "_b200_frozen", None)
+        if frozen is not None:
+            return frozen["layers"]
+        return self._fold_affine_uncached()
+
+    def b200_freeze(self):
+        """Inference with final weights: fold the BN affine once and keep the packed tensor-core weight images
+        ("plans", include/b200_pointnet2.h) per call shape.  The caller promises not to modify parameters or BN
+        statistics until b200_unfreeze() / train()."""
+        layers = self._fold_affine_uncached() if not any(m.training for m in self.modules()) else None
+        object.__setattr__(self, "_b200_frozen", {"layers": layers, "plans": {}} if layers is not None else None)
+        return layers is not None
+
+    def b200_unfreeze(self):
+        object.__setattr__(self, "_b200_frozen", None)
+
+    def train(self, mode=True):
+        if mode:
+            self.b200_unfreeze()
+        return super().train(mode)
+
+    def b200_plan(self, layers, C_feat, use_xyz, row_output=False, plain_rows=False):
+        """Cached packed weights for `layers` (a slice of the frozen stack) or None when not frozen."""
+        frozen = getattr(self, "_b200_frozen", None)
+        if frozen is None or frozen["layers"] is None:
+            return None
+        import pointnet2._ext as _ext
+        key = (layers[0][0].data_ptr(), len(layers), int(C_feat), bool(use_xyz), bool(row_output), bool(plain_rows),
+               os.environ.get("B200_SA_TC_FACTOR", ""), str(layers[0][0].device))
+        if key not in frozen["plans"]:
+            frozen["plans"][key] = _ext.mlp_plan(layers, C_feat, use_xyz, row_output=row_output, plain_rows=plain_rows)
+        return frozen["plans"][key]
+
+    def forward(self, x):
+        """Eval mode, no gradient, CUDA: the whole stack as row MLPs on the tensor-core kernel (one launch per run of
+        layers, activations between the layers of a run never leave the SM); otherwise nn.Sequential."""
+        if (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and os.environ.get("B200_SA_FUSED", "1") != "0" and
+                not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))):
+            layers = self.fold_affine()
+            if layers:
+                out = self._rows_forward(x, layers)
+                if out is not None:
+                    return out
+        return super().forward(x)
+
+    def _rows_forward(self, x, layers):
+        import pointnet2._ext as _ext
+        B, C, H, W = x.shape
+        if B * H * W == 0 or any(w.size(0) > 256 for w, _, _ in layers) or layers[0][0].size(1) != C:
+            return None
+        groups = _ext.split_row_groups(layers)
+        ld = (C + 3) // 4 * 4
+        rows = _ext.transpose_cn(x.contiguous().view(B, C, H * W), ld=ld)       # (B, H*W, ld)
+        chan = C
+        for gi, grp in enumerate(groups):
+            last = gi == len(groups) - 1
+            plan = self.b200_plan(grp, chan, False, row_output=True, plain_rows=True)
+            out_cm, out_pm = _ext.row_mlp_forward(rows, grp, relu_last=True, want_cm=last, want_pm=not last, plan=plan,
+                                                  channels=chan)
+            rows, chan = out_pm, grp[-1][0].size(0)
+        return out_cm.view(B, chan, H, W)
 
     def _fold_affine_uncached(self):
         triples = []
@@ -156,6 +216,22 @@ class SharedMLP(nn.Sequential):
                 shift = cb.clone() if cb is not None else torch.zeros_like(scale)
             triples.append((w.float(), scale.float().contiguous(), shift.float().contiguous()))
         return triples
+
+
+def freeze_inference(model):
+    """Freeze every SharedMLP of `model` for inference with final weights (see SharedMLP.b200_freeze): call after
+    model.eval() and after the checkpoint is loaded.  Returns the number of stacks frozen."""
+    n = 0
+    for m in model.modules():
+        if isinstance(m, SharedMLP) and m.b200_freeze():
+            n += 1
+    return n
+
+
+def unfreeze(model):
+    for m in model.modules():
+        if isinstance(m, SharedMLP):
+            m.b200_unfreeze()
 
 
 def set_bn_momentum_default(bn_momentum):

@@ -49,18 +49,26 @@ def allreduce_gradients(model, average=True):
     sharded, and after backward the 1.06 M gradient elements (4.26 MB fp32) are summed in ONE flat bucket -- a single
     latency-bound all-reduce per step instead of one per parameter (the reference uses nn.DataParallel's reduce_add).
     BatchNorm statistics stay per replica, as with DataParallel.  Returns the number of elements reduced."""
-    params = [p for p in model.parameters() if p.grad is not None]
+    # EVERY trainable parameter takes part, in module order, with zeros standing in for a missing gradient: the bucket
+    # layout must be identical on all ranks even when a rank's shard left a head unused (no labelled object -> no grad)
+    params = [p for p in model.parameters() if p.requires_grad]
     if not params:
         return 0
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dtypes = {p.dtype for p in params}
+    if len(dtypes) != 1:
+        raise TypeError("allreduce_gradients: one flat bucket needs a single parameter dtype, got %s" % sorted(map(str, dtypes)))
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         if average:
             flat /= dist.get_world_size()
     off = 0
     for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
     return int(flat.numel())
 

@@ -151,6 +151,65 @@ int b200pn2_interp_mlp_forward(int B, int m_known, int M, int nsample, int C, co
                                const float *rel_xyz, int num_layers, const b200_mlp_layer *layers, float *out,
                                void *workspace, size_t workspace_bytes, b200_stream_t stream);
 
+
+/* ---- packed-weight plans -------------------------------------------------------------------------------------------
+ * The tensor-core kernels consume SharedMLP weights split into TF32 hi/lo parts and laid out as the shared-memory image
+ * of their pipeline stages.  Packing is a function of the weights only, so a module packs ONCE into device memory it
+ * owns (a "plan") and passes it to the *_planned / row entries below; with plan == NULL the library packs into
+ * stream-ordered scratch on every call.  A plan is valid for exactly the (C_feat, use_xyz, layers, row_output,
+ * plain_rows) it was built for and until the weights / folded BN affine change (the first layer's scale is baked in
+ * when that layer is factorised).
+ *   row_output  0: max-pooled stacks (sa_forward, interp_mlp_forward)   1: row stacks (fp_rows_forward, row_mlp_forward)
+ *   plain_rows  1: the stack reads plain rows (row_mlp_forward): no xyz column permutation, never factorised
+ * b200pn2_mlp_plan_bytes returns 0 when the tensor-core kernel does not take the stack.                              */
+size_t b200pn2_mlp_plan_bytes(int C_feat, int use_xyz, int num_layers, const b200_mlp_layer *layers, int row_output,
+                              int plain_rows);
+int b200pn2_mlp_plan_build(int C_feat, int use_xyz, int num_layers, const b200_mlp_layer *layers, int row_output,
+                           int plain_rows, void *plan, size_t plan_bytes, b200_stream_t stream);
+
+/* b200pn2_sa_forward / b200pn2_interp_mlp_forward with a caller-owned plan (NULL, 0: pack per call).                 */
+int b200pn2_sa_forward_planned(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                               const float *xyz, const float *features, const float *features_pm, const float *new_xyz,
+                               const int32_t *idx_in, int num_layers, const b200_mlp_layer *layers, float *out,
+                               float *out_pm, int32_t *idx_out, void *workspace, size_t workspace_bytes,
+                               const void *plan, size_t plan_bytes, b200_stream_t stream);
+int b200pn2_interp_mlp_forward_planned(int B, int m_known, int M, int nsample, int C, const float *known_feats,
+                                       const float *known_feats_pm, const int32_t *idx3, const float *weight3,
+                                       const float *rel_xyz, int num_layers, const b200_mlp_layer *layers, float *out,
+                                       void *workspace, size_t workspace_bytes, const void *plan, size_t plan_bytes,
+                                       b200_stream_t stream);
+
+/* ---- feature propagation rows -> SharedMLP rows (PointnetFPModule.forward, pointnet2_modules.py:377-422) -------------
+ * Replaces three_interpolate -> torch.cat([interpolated, unknow_feats]) -> SharedMLP (1x1 conv + BN + ReLU):
+ * row q of scene b = [sum_t weight3[b,q,t] * known_feats_pm[b, idx3[b,q,t], :] (C2) | skip_feats_pm[b,q,:] (C1)]
+ * runs through the stack; one output row per q.  Blend rounding = three_interpolate's (interpolate_gpu.cu:100-104).
+ *   known_feats_pm (B,m_known,C2), skip_feats_pm (B,n,C1) or NULL (C1 = 0), idx3 / weight3 (B,n,3)
+ *   out (B,cout,n) channel-major and/or out_pm (B,n,cout) point-major (either may be NULL)
+ *   hidden widths multiples of 32 and <= 128, last width <= 256 (wider stacks: one call per layer, chained through
+ *   b200pn2_row_mlp_forward);  relu_last: ReLU after the last layer of THIS call.                                    */
+int b200pn2_fp_rows_forward(int B, int n, int m_known, int C2, int C1, const float *known_feats_pm,
+                            const float *skip_feats_pm, const int32_t *idx3, const float *weight3, int num_layers,
+                            const b200_mlp_layer *layers, int relu_last, float *out, float *out_pm, const void *plan,
+                            size_t plan_bytes, b200_stream_t stream);
+
+/* ---- row MLP: 1x1-conv stacks on plain rows (FP layers 2.., voting_module.py:38-65, proposal_module.py:98-123,
+ * grid_conv_module.py:108-115) ------------------------------------------------------------------------------------
+ *   x_pm (S*R, ld) point-major rows of C channels (ld = 0: C; rows whose stride is a multiple of 4 floats on a
+ *   16-byte-aligned base are read with vector loads), S scenes of R rows;  out (S,cout,R) channel-major and/or
+ *   out_pm (S*R,cout).                                                                                              */
+int b200pn2_row_mlp_forward(int S, int R, int C, int ld, const float *x_pm, int num_layers,
+                            const b200_mlp_layer *layers, int relu_last, float *out, float *out_pm, const void *plan,
+                            size_t plan_bytes, b200_stream_t stream);
+
+/* (B,C,N) channel-major -> (B,N,out_ld) point-major (the layout the fused kernels gather from); out_ld = 0: C,
+ * otherwise >= C with zero-filled padding columns.                                                                  */
+int b200pn2_transpose_cn(int B, int C, int N, const float *in_cm, float *out_pm, int out_ld, b200_stream_t stream);
+
+/* Tensor-pipe work issued by the fused kernels since the last reset: sum over tcgen05.mma instructions of their N
+ * (each is a 128 x N x 8 TF32 multiply-add block = 2048*N FLOP).  Synchronises the device.  bench.py: executed TF32
+ * FLOP/s of the roofline.                                                                                          */
+int b200pn2_sa_tensor_work(unsigned long long *mma_n_columns, int reset);
+
 #ifdef __cplusplus
 }
 #endif

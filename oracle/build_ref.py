@@ -5,10 +5,12 @@ Recipe (no reference build system is run; no reference source enters the repo):
     /root/reference into two torch extension modules:
         oracle/_ref/pointnet2/_ext.so                      (pointnet2/_ext_src/src/*.{cpp,cu})
         oracle/_ref/pcdet/ops/iou3d_nms/iou3d_nms_cuda.so  (OpenPCDet/pcdet/ops/iou3d_nms/src/*)
-  * the reference's Python operator modules / callers are *installed* (copied, like
+  * the reference's Python operator modules are *installed* (copied, like
     `pip install --target` would) beside them so the stock code path can be run on
-    the GPU box, where /root/reference does not exist.
-oracle/_ref/ is git-ignored (never enters history) but travels with gpurun.
+    the GPU box, where /root/reference does not exist; the reference's APPLICATION
+    python (models/, utils/, dataset configs: the callers above the operator boundary)
+    is installed into baseline/_ref/ (see install_python).
+oracle/_ref/ and baseline/_ref/ are git-ignored (never enter history) but travel with gpurun.
 
 Used by: tests (cross-check oracle == reference CUDA on the GPU box; reference CPU
 BEV IoU golden vectors here), bench.py --impl reference.  Never by the product.
@@ -80,25 +82,40 @@ def build_ext(name, src_dir, so, extra_inc=()):
     return so
 
 
+APP_OUT = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
 def install_python():
-    """Install (copy) the reference's python operator modules and their callers."""
-    def cp(rel_src, rel_dst):
-        dst = os.path.join(OUT, rel_dst)
+    """Install (copy, like `pip install --target` would) the reference's python files.
+
+    oracle/_ref/   the reference OPERATOR stack: its python operator modules beside the two extensions built above
+                   (the checker of the GPU tests, and the stack under `bench.py --impl reference`);
+    baseline/_ref/ the reference APPLICATION: models/, utils/, the two dataset configs -- pure python ABOVE the operator
+                   boundary (votenet_iou_branch.py, the loss helpers ...).  Both bench arms and the integration tests run
+                   these unmodified callers, once on the drop-in operators and once on oracle/_ref.
+    Both directories are git-ignored (no reference source enters the history) and travel with gpurun."""
+    def cp(rel_src, dst_root, rel_dst=None):
+        dst = os.path.join(dst_root, rel_dst or rel_src)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         shutil.copyfile(os.path.join(REF, rel_src), dst)
 
     for f in ("pointnet2_utils.py", "pointnet2_modules.py", "pytorch_utils.py"):
-        cp("pointnet2/" + f, "pointnet2/" + f)
+        cp("pointnet2/" + f, OUT)
     open(os.path.join(OUT, "pointnet2", "__init__.py"), "a").close()
-    cp("OpenPCDet/pcdet/ops/iou3d_nms/iou3d_nms_utils.py", "pcdet/ops/iou3d_nms/iou3d_nms_utils.py")
-    cp("OpenPCDet/pcdet/utils/common_utils.py", "pcdet/utils/common_utils.py")
+    cp("OpenPCDet/pcdet/ops/iou3d_nms/iou3d_nms_utils.py", OUT, "pcdet/ops/iou3d_nms/iou3d_nms_utils.py")
+    cp("OpenPCDet/pcdet/utils/common_utils.py", OUT, "pcdet/utils/common_utils.py")
     for d in ("pcdet", "pcdet/ops", "pcdet/ops/iou3d_nms", "pcdet/utils"):
         open(os.path.join(OUT, d, "__init__.py"), "a").close()
-    for f in ("backbone_module.py", "voting_module.py", "proposal_module.py", "grid_conv_module.py",
-              "votenet_iou_branch.py", "loss_helper_iou.py"):
-        cp("models/" + f, "models/" + f)
-    for f in ("box_util.py", "nn_distance.py"):
-        cp("utils/" + f, "utils/" + f)
+    for stale in ("models", "utils"):  # round-1 layout kept the callers inside oracle/_ref
+        shutil.rmtree(os.path.join(OUT, stale), ignore_errors=True)
+    for d in ("models", "utils"):
+        for f in sorted(os.listdir(os.path.join(REF, d))):
+            if f.endswith(".py"):
+                cp(d + "/" + f, APP_OUT)
+    cp("scannet/model_util_scannet.py", APP_OUT)
+    cp("scannet/meta_data/scannet_means.npz", APP_OUT)
+    cp("sunrgbd/model_util_sunrgbd.py", APP_OUT)
+    cp("sunrgbd/sunrgbd_utils.py", APP_OUT)
 
 
 def dump_fma():
@@ -125,12 +142,16 @@ def dump_fma():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dump-fma", action="store_true")
+    ap.add_argument("--python-only", action="store_true", help="(re)install the python files, keep the built extensions")
     a = ap.parse_args()
     if not os.path.isdir(REF):
         print("reference tree %s not present; using prebuilt oracle/_ref if any" % REF)
         return 0
     if a.dump_fma:
         dump_fma()
+        return 0
+    if a.python_only:
+        install_python()
         return 0
     src1 = os.path.join(REF, "pointnet2/_ext_src/src")
     so1 = build_ext("_ext", src1, os.path.join(OUT, "pointnet2", "_ext.so"),

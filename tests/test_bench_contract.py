@@ -1,4 +1,4 @@
-"""The committed bench lines (profiles/r1c_bench_*.json, produced by bench.py on a B200) carry every key the measurement
+"""The committed bench lines (profiles/r2_bench_*.json, produced by bench.py on a B200) carry every key the measurement
 contract names, and their derived numbers are consistent (no GPU needed: this checks the artefacts, not the device)."""
 import json
 import os
@@ -16,14 +16,20 @@ def _line(name):
 
 
 def test_product_line_has_the_contract_keys():
-    d = _line("r1c_bench_1gpu.json")
+    d = _line("r2_bench_1gpu.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
     assert d["unit"] == "scenes/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
     assert d["vs_baseline"] is None          # BASELINE.json publishes no number for this metric
     assert d["warmup"] >= 3 and d["n_gpus"] == 1 and d["gpu_launches"] > 0
-    assert "workload" in d["config"] and "model" not in d["config"]
+    assert "workload" in d["config"] and d["config"]["model"].startswith("models/votenet_iou_branch.py")
+    assert "lanes" not in d["config"] and "host_enqueue_ms_per_step" not in d["config"]   # arm-specific -> impl_options
+    assert d["impl_options"]["callers"] == "reference"
+    assert d["check"]["ok"] is True and d["check"]["indices_exact"] is True
+    t = d["roofline_tensor"]
+    assert t["bound"] == "tensor" and abs(t["frac"] - t["achieved"] / t["peak"]) <= 1e-3 and t["executed_tf32_flop_per_step"] > 0
+    assert d["roofline"]["latency"]["us_per_iteration"] > 0 and len(d["per_op"]) >= 8
     # value is whole-job throughput: scenes per step / time per step
     scenes = d["config"]["scenes_per_gpu_per_step"] * d["n_gpus"]
     assert abs(d["value"] - scenes / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-3
@@ -41,37 +47,32 @@ def test_product_line_has_the_contract_keys():
 
 
 def test_reference_arm_line():
-    d = _line("r1c_bench_reference_arm.json")
-    p = _line("r1c_bench_1gpu.json")
+    d = _line("r2_bench_reference_arm.json")
+    p = _line("r2_bench_1gpu.json")
     assert d["impl"] == "reference"
     for k in ("metric", "unit", "higher_is_better"):
         assert d[k] == p[k]
-    assert d["config"]["workload"] == p["config"]["workload"]
+    assert d["config"] == p["config"]           # same workload, same model file: only impl_options differ
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["unit"] == d["unit"] and d["e2e"]["value"] > 0
 
 
 def test_two_gpu_line_scales():
-    d = _line("r1c_bench_2gpu.json")
-    p = _line("r1c_bench_1gpu.json")
+    d = _line("r2_bench_2gpu.json")
+    p = _line("r2_bench_1gpu.json")
     assert d["n_gpus"] == 2 and d["scaling"] == "weak"
     assert d["value"] > 1.8 * p["value"]     # scene-sharded, no data-path collective
 
 
-def test_sa_hbm_view_on_the_committed_breakdown():
-    """bench.sa_hbm_view (pure function): fused-bytes and unfused-equivalent HBM views of the SA launches."""
+def test_fps_latency_view_is_a_pure_function_of_the_measurement():
+    """bench.fps_latency_view: microseconds per dependent iteration against the stated per-iteration latency floor."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    d = _line("r1c_bench_1gpu.json")
-    sa = {k: v for k, v in d["breakdown_ms"].items() if k.startswith("sa_forward")}
-    assert len(sa) == 5
-    v = bench.sa_hbm_view(sa, d["roofline"]["peak"], d["config"]["scenes_per_gpu_per_step"])
-    assert v["bound"] == "hbm" and abs(v["frac"] - v["achieved"] / v["peak"]) < 1e-3
-    u = v["unfused_equivalent"]
-    assert abs(u["gb_per_step"] - 1.48 * 8) < 0.05           # 1.47-1.48 GB per scene (BASELINE.md section 2)
-    assert u["frac"] > 1.0                                    # the fused layers beat the unfused pipeline's HBM bound
-    # unknown shapes: the fused-bytes view only
-    w = bench.sa_hbm_view({"sa_forward[N=9,M=3,ns=8]": {"ms": 0.1, "calls_per_step": 1, "alg_bytes": 1000}}, 6000.0, 1)
-    assert "unfused_equivalent" not in w
+    v = bench.fps_latency_view("furthest_point_sampling[N=40000,m=2048]", {"ms": 2.047}, 1965.0)
+    assert v["bound"] == "latency" and v["iterations"] == 2047 and abs(v["us_per_iteration"] - 1.0) < 1e-6
+    assert abs(v["floor_us_per_iteration"] - bench.FPS_FLOOR_CYCLES_CLUSTER / 1965.0) < 1e-4
+    assert abs(v["frac_of_floor"] - v["floor_us_per_iteration"] / v["us_per_iteration"]) < 1e-3
+    w = bench.fps_latency_view("furthest_point_sampling[N=1024,m=512]", {"ms": 0.1533}, 1965.0)
+    assert abs(w["floor_us_per_iteration"] - bench.FPS_FLOOR_CYCLES_SINGLE_CTA / 1965.0) < 1e-4

@@ -61,59 +61,12 @@ def test_fps_every_cluster_size_agrees(pkg, orc, monkeypatch):
             "np.save('/tmp/_fps_out.npy',e.furthest_point_sampling(x,300).cpu().numpy())") % os.path.dirname(pkg.PKG_DIR)
     for cs in (1, 2, 4, 8, 16):
         for th in (32, 64, 128, 256, 512):
-            env = dict(os.environ, B200_FPS_CLUSTER=str(cs), B200_FPS_THREADS=str(th), B200_FPS_PRUNE="0")
+            env = dict(os.environ, B200_FPS_CLUSTER=str(cs), B200_FPS_THREADS=str(th))
             r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
             if r.returncode != 0 and "needs a scratch buffer" in (r.stderr + r.stdout):
                 continue  # this (cluster, threads) pair cannot hold the cloud in registers
             assert r.returncode == 0, r.stderr[-2000:]
             assert np.array_equal(np.load("/tmp/_fps_out.npy"), ref), "cluster=%d threads=%d" % (cs, th)
-
-
-@pytest.mark.parametrize("name", sorted(CASES))
-def test_fps_pruned_kernel_bit_exact(pkg, orc, name, monkeypatch):
-    """The Morton-ordered, sphere-pruned kernel (fps_pruned.cu; default for large clouds) forced on for every case,
-    including duplicates (distance ties), origin points (skipped) and npoint > N."""
-    import pointnet2._ext as ext
-    monkeypatch.setenv("B200_FPS_PRUNE", "1")
-    kw, npoint, _, _ = CASES[name]
-    xyz = cases.cloud(**kw)
-    fps = ext.furthest_point_sampling(dev(xyz), npoint).cpu().numpy()
-    assert np.array_equal(fps, orc.furthest_point_sampling(xyz, npoint)), "pruned FPS indices differ"
-
-
-def test_fps_pruned_non_finite_and_far_points(pkg, orc, monkeypatch):
-    """inf / NaN coordinates disable pruning for their block only; far outliers stretch the Morton box."""
-    import pointnet2._ext as ext
-    monkeypatch.setenv("B200_FPS_PRUNE", "1")
-    xyz = cases.cloud(11, 2, 5000, dup_frac=0.05)
-    xyz[0, 17] = (np.inf, 0.5, 0.5)
-    xyz[0, 400] = (np.nan, 1.0, 1.0)
-    xyz[1, 3] = (900.0, -700.0, 50.0)
-    xyz[1, 4999] = (-1e4, 1e4, 0.0)
-    fps = ext.furthest_point_sampling(dev(xyz), 256).cpu().numpy()
-    assert np.array_equal(fps, orc.furthest_point_sampling(xyz, 256))
-
-
-def test_fps_pruned_every_cluster_size_agrees(pkg, orc):
-    import os
-    import subprocess
-    import sys
-    xyz = cases.cloud(7, 2, 9000, dup_frac=0.2, origin_frac=0.01)
-    ref = orc.furthest_point_sampling(xyz, 300)
-    np.save("/tmp/_fpp_xyz.npy", xyz)
-    code = ("import importlib,sys,numpy as np,torch;sys.path.insert(0,%r);p=importlib.import_module('3dioumatch_b200');"
-            "p.install_dropin();import pointnet2._ext as e;x=torch.from_numpy(np.load('/tmp/_fpp_xyz.npy')).cuda();"
-            "n0=p.cabi().launch_count();o=e.furthest_point_sampling(x,300).cpu().numpy();"
-            "print('LAUNCHES',p.cabi().launch_count()-n0);np.save('/tmp/_fpp_out.npy',o)") % os.path.dirname(pkg.PKG_DIR)
-    ran = 0
-    for cs in (1, 2, 4, 8, 16):
-        for th in (256, 512):
-            env = dict(os.environ, B200_FPS_PRUNE="1", B200_FPS_PRUNE_CLUSTER=str(cs), B200_FPS_PRUNE_THREADS=str(th))
-            r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-            assert r.returncode == 0, r.stderr[-2000:]
-            assert np.array_equal(np.load("/tmp/_fpp_out.npy"), ref), "cluster=%d threads=%d" % (cs, th)
-            ran += int(r.stdout.split("LAUNCHES")[1].split()[0]) > 3  # pre-pass + sort + kernel (fps.cu fallback = 1)
-    assert ran >= 6
 
 
 def test_fps_scannet_shape_full_size(pkg, orc):

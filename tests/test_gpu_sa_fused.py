@@ -174,64 +174,135 @@ def test_module_training_path_backward(pkg):
     assert net.mlp_module.layer0.conv.weight.grad is not None
 
 
-def test_fp_module(pkg, orc, tr):
-    """PointnetFPModule (three_nn + three_interpolate + SharedMLP) vs the fp32 restatement."""
-    import pointnet2_modules as M
-    import pointnet2.pytorch_utils as pt
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.set_float32_matmul_precision("highest")
-    rng = np.random.default_rng(0)
-    B, n, m, C1, C2 = 2, 512, 256, 24, 40
-    unknown = cases.cloud(1, B, n)
-    known = unknown[:, :m].copy()
-    uf = rng.standard_normal((B, C1, n)).astype(np.float32)
-    kf = rng.standard_normal((B, C2, m)).astype(np.float32)
-    layers = cases.mlp_params(3, [C1 + C2, 48, 32])
-    fp = M.PointnetFPModule(mlp=[C1 + C2, 48, 32]).cuda().eval()
+def _load_mlp(mlp, layers):
     with torch.no_grad():
         for i, ly in enumerate(layers):
-            blk = getattr(fp.mlp, "layer%d" % i)
+            blk = getattr(mlp, "layer%d" % i)
             blk.conv.weight.copy_(dev(ly["weight"]).view_as(blk.conv.weight))
             blk.bn.bn.weight.copy_(dev(ly["gamma"])); blk.bn.bn.bias.copy_(dev(ly["beta"]))
             blk.bn.bn.running_mean.copy_(dev(ly["mean"])); blk.bn.bn.running_var.copy_(dev(ly["var"]))
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 512, 256, 24, 64, [48, 32], "small, hidden layer fused in one launch"),
+    (2, 512, 256, 256, 256, [256, 256], "FP1 of the VoteNet backbone (backbone_module.py:71)"),
+    (8, 1024, 512, 256, 256, [256, 256], "FP2 at the bench batch"),
+    (1, 300, 7, 0, 32, [64], "no skip features, fewer known points than unknown, ragged rows"),
+])
+def test_fp_module(pkg, orc, tr, shape, monkeypatch):
+    """PointnetFPModule (three_nn -> inverse-distance blend -> concat skip -> SharedMLP, pointnet2_modules.py:377-422):
+    the fused path (rows built in the tensor-core kernel's producers, no interpolated / concatenated tensor in HBM)
+    against the fp32 restatement, every element, 1e-5; and the op-by-op path (B200_SA_FUSED=0) on the same module."""
+    import pointnet2_modules as M
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, n, m, C1, C2, spec, _ = shape
+    rng = np.random.default_rng(0)
+    unknown = cases.cloud(1, B, n)
+    known = unknown[:, :m].copy() if m <= n else cases.cloud(2, B, m)
+    uf = rng.standard_normal((B, C1, n)).astype(np.float32) if C1 else None
+    kf = rng.standard_normal((B, C2, m)).astype(np.float32)
+    layers = cases.mlp_params(3, [C1 + C2] + spec)
+    fp = M.PointnetFPModule(mlp=[C1 + C2] + spec).cuda().eval()
+    _load_mlp(fp.mlp, layers)
+    launches0 = pkg.cabi().launch_count()
+    with torch.no_grad():
         got = fp(dev(unknown), dev(known), dev(uf), dev(kf)).cpu().numpy()
+    assert pkg.cabi().launch_count() - launches0 >= 3  # three_nn + transposes + the fused rows kernel(s): not torch convs
     ref = tr.fp_forward(unknown, known, uf, kf, layers)
-    err = np.abs(got - ref)
-    # three_nn / three_interpolate are ours (bit-exact vs the oracle, tested above); the 1x1 convs are cuDNN's, whose
-    # fp32 algorithm choice (and summation order) is not under our control -> 1e-4 on O(1) features
+    assert_close(got, ref)
+    monkeypatch.setenv("B200_SA_FUSED", "0")
+    with torch.no_grad():
+        unfused = fp(dev(unknown), dev(known), dev(uf), dev(kf)).cpu().numpy()
+    err = np.abs(unfused - ref)  # cuDNN's fp32 algorithm choice is not under our control -> 1e-4 for this path only
     assert (err <= 1e-4 + 1e-4 * np.abs(ref)).all(), float(err.max())
 
 
-def test_grid_interp_mlp_max_fused_equals_generic(pkg, monkeypatch):
+@pytest.mark.parametrize("spec", [[259, 128, 128, 128], [128, 128, 128, 97], [256, 256, 256, 3], [64, 32], [20, 256]])
+def test_shared_mlp_forward_rows(pkg, tr, spec):
+    """pt_utils.SharedMLP.forward in eval mode = fused row MLPs (1x1-conv heads, grid_conv_module.py:108-113) vs the fp32
+    restatement, every element, 1e-5; widths that are no multiple of 32 / of 4, >128-wide layers chained."""
+    import pointnet2.pytorch_utils as pt
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, spec[0], 50, 16)).astype(np.float32)
+    layers = cases.mlp_params(7, spec)
+    mlp = pt.SharedMLP(list(spec), bn=True).cuda().eval()
+    _load_mlp(mlp, layers)
+    launches0 = pkg.cabi().launch_count()
+    with torch.no_grad():
+        got = mlp(dev(x))
+    assert pkg.cabi().launch_count() > launches0, "SharedMLP.forward did not reach libb200pc.so"
+    ref = tr.shared_mlp(torch.from_numpy(x), layers).numpy()
+    assert got.shape == ref.shape
+    assert_close(got.cpu().numpy(), ref)
+
+
+def test_frozen_plans_equal_per_call_packing(pkg, orc, tr):
+    """freeze_inference(): packed weights cached per module (no tc_pack_weights_kernel in steady state) -- bit-identical
+    outputs, fewer launches; unfreezing picks up a weight change made through .data (the reference's EMA idiom)."""
+    import pointnet2_modules as M
+    import pointnet2.pytorch_utils as pt
+    torch.manual_seed(0)
+    net = M.PointnetSAModuleVotes(npoint=256, radius=0.4, nsample=32, mlp=[128, 128, 128, 256], use_xyz=True,
+                                  normalize_xyz=True).cuda().eval()
+    xyz = dev(cases.cloud(3, 2, 2048))
+    feats = torch.randn(2, 128, 2048, device="cuda")
+    with torch.no_grad():
+        _, base, _ = net(xyz, feats)
+        c0 = pkg.cabi().launch_count()
+        net(xyz, feats)
+        per_call = pkg.cabi().launch_count() - c0
+        assert pt.freeze_inference(net) == 1
+        _, first, _ = net(xyz, feats)          # builds the plan
+        c0 = pkg.cabi().launch_count()
+        _, frozen, _ = net(xyz, feats)
+        steady = pkg.cabi().launch_count() - c0
+        assert torch.equal(base, first) and torch.equal(base, frozen)
+        assert steady < per_call, (steady, per_call)
+        net.mlp_module.layer0.conv.weight.data.mul_(1.5)   # no version bump
+        _, stale, _ = net(xyz, feats)
+        assert torch.equal(stale, frozen)                  # frozen = the caller's promise; documented
+        pt.unfreeze(net)
+        _, fresh, _ = net(xyz, feats)
+        assert not torch.equal(fresh, frozen)
+
+
+def test_grid_interp_mlp_max_fused_vs_oracle(pkg, orc, tr, monkeypatch):
     """IoU-branch sampler (grid_conv_module.py:87-113 shapes: K*64 grid points vs 1024 seeds, MLP [259,128,128,128]):
-    fused tensor-core kernel vs the op-by-op path on the same inputs."""
+    fused tensor-core kernel vs the oracle stack (C three_nn / three_interpolate + fp32 torch MLP), every element 1e-5,
+    and vs the op-by-op path on the same inputs."""
     import pointnet2.pointnet2_utils as U
     import pointnet2.pytorch_utils as pt
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
     B, K, m, C = 2, 64, 1024, 256
-    seeds = torch.rand(B, m, 3, device="cuda") * 6
-    feats = torch.randn(B, C, m, device="cuda")
-    grid = torch.rand(B, K * 64, 3, device="cuda") * 6
-    dist, idx = U.three_nn(grid, seeds)
-    w = 1.0 / (dist + 1e-8)
-    w = (w / w.sum(2, keepdim=True)).contiguous()
-    rel = (torch.rand(B, K * 64, 3, device="cuda") - 0.5).contiguous()
-    mlp = pt.SharedMLP([C + 3, 128, 128, 128], bn=True).cuda()
-    for mod in mlp.modules():
-        if isinstance(mod, torch.nn.BatchNorm2d):
-            mod.running_mean.normal_(0, 0.2)
-            mod.running_var.uniform_(0.5, 1.5)
-    mlp.eval()
+    seeds = (rng.random((B, m, 3)) * 6).astype(np.float32)
+    feats = rng.standard_normal((B, C, m)).astype(np.float32)
+    grid = (rng.random((B, K * 64, 3)) * 6).astype(np.float32)
+    rel = (rng.random((B, K * 64, 3)) - 0.5).astype(np.float32)
+    layers = cases.mlp_params(9, [C + 3, 128, 128, 128])
+    mlp = pt.SharedMLP([C + 3, 128, 128, 128], bn=True).cuda().eval()
+    _load_mlp(mlp, layers)
+    # oracle stack
+    d2, oidx = orc.three_nn(grid, seeds)
+    ow = 1.0 / (torch.sqrt(torch.from_numpy(d2)) + 1e-8)
+    ow = (ow / ow.sum(2, keepdim=True)).numpy()
+    interp = torch.from_numpy(orc.three_interpolate(feats, oidx, ow)).view(B, C, K, 64)
+    x = torch.cat([torch.from_numpy(rel).transpose(1, 2).contiguous().view(B, 3, K, 64), interp], 1)
+    ref = torch.nn.functional.max_pool2d(tr.shared_mlp(x, layers), kernel_size=[1, 64]).squeeze(-1).numpy()
     with torch.no_grad():
-        fused = U.grid_interp_mlp_max(feats, idx, w, rel, 64, mlp)
+        dist, idx = U.three_nn(dev(grid), dev(seeds))
+        assert np.array_equal(idx.cpu().numpy(), oidx)
+        w = 1.0 / (dist + 1e-8)
+        w = (w / w.sum(2, keepdim=True)).contiguous()
+        fused = U.grid_interp_mlp_max(dev(feats), idx, w, dev(rel), 64, mlp)
         monkeypatch.setenv("B200_SA_FUSED", "0")
-        generic = U.grid_interp_mlp_max(feats, idx, w, rel, 64, mlp)
+        generic = U.grid_interp_mlp_max(dev(feats), idx, w, dev(rel), 64, mlp)
     assert fused.shape == (B, 128, K)
-    err = (fused - generic).abs()
-    assert bool((err <= 2e-5 + 2e-5 * generic.abs()).all()), float(err.max())
+    assert_close(fused.cpu().numpy(), ref)
+    err = (generic.cpu().numpy() - ref)
+    assert (np.abs(err) <= 1e-4 + 1e-4 * np.abs(ref)).all()
 
 
 def test_msg_modules_forward_backward(pkg):

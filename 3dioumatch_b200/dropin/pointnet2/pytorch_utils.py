@@ -11,6 +11,11 @@ import os
 import torch
 import torch.nn as nn
 
+try:  # bound at import time: callers may load several operator stacks into one process (3dioumatch_b200/refapp.py)
+    from . import _ext
+except ImportError:  # imported flat (`import pytorch_utils`), as the reference's pointnet2_modules.py does
+    import _ext
+
 _DEFAULT_ACT = nn.ReLU(inplace=True)
 
 
@@ -146,7 +151,6 @@ class SharedMLP(nn.Sequential):
         frozen = getattr(self, "_b200_frozen", None)
         if frozen is None or frozen["layers"] is None:
             return None
-        import pointnet2._ext as _ext
         key = (layers[0][0].data_ptr(), len(layers), int(C_feat), bool(use_xyz), bool(row_output), bool(plain_rows),
                os.environ.get("B200_SA_TC_FACTOR", ""), str(layers[0][0].device))
         if key not in frozen["plans"]:
@@ -166,7 +170,6 @@ class SharedMLP(nn.Sequential):
         return super().forward(x)
 
     def _rows_forward(self, x, layers):
-        import pointnet2._ext as _ext
         B, C, H, W = x.shape
         if B * H * W == 0 or any(w.size(0) > 256 for w, _, _ in layers) or layers[0][0].size(1) != C:
             return None
@@ -225,6 +228,9 @@ def freeze_inference(model):
     for m in model.modules():
         if isinstance(m, SharedMLP) and m.b200_freeze():
             n += 1
+        head = getattr(m, "_b200_head", None)   # 1x1-conv heads of the drop-in caller mirrors (dropin_callers/)
+        if head is not None and not m.training:
+            head.freeze()
     return n
 
 
@@ -232,6 +238,9 @@ def unfreeze(model):
     for m in model.modules():
         if isinstance(m, SharedMLP):
             m.b200_unfreeze()
+        head = getattr(m, "_b200_head", None)
+        if head is not None:
+            head.unfreeze()
 
 
 def set_bn_momentum_default(bn_momentum):

@@ -29,7 +29,7 @@ FAST_CALLERS_DIR = os.path.join(PKG_DIR, "dropin_callers")
 # top-level module names both stacks (and the application) define
 _OWNED = ("pointnet2", "pointnet2_modules", "pointnet2_utils", "pytorch_utils", "pcdet", "models", "utils", "scannet",
           "sunrgbd", "_ext", "iou3d_nms_cuda", "nn_distance", "box_util", "pc_util", "nms", "model_util_scannet",
-          "model_util_sunrgbd")
+          "model_util_sunrgbd", "_b200_rows")
 # optional third-party imports of reference files that are not on the measured path (plotting / mesh IO)
 _STUBS = ("trimesh", "matplotlib", "matplotlib.pyplot", "plyfile", "cv2", "mayavi", "scipy.io")
 
@@ -137,6 +137,8 @@ def build_votenet(ns, dataset="scannet", num_proposal=256, seed=1, device="cuda"
         if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
             m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
             m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) * 0.5 + 0.75)
+    if hasattr(net.backbone_net, "prefetch_proposals") and net.pnet.sampling == "seed_fps":
+        net.backbone_net.prefetch_proposals = num_proposal   # drop-in backbone mirror: seed FPS joins the prefetched chain
     net = net.to(device)
     return (net.train() if train else net.eval()), cfg
 

@@ -186,3 +186,44 @@ def test_c_graph_replay_lanes_frozen_throughput_policy(world):
     for i, (e, g) in enumerate(zip(eager, outs)):
         for k in out_keys:
             assert torch.equal(e[k], g[k]), "step %d: %s differs between eager and graph replay" % (i, k)
+
+
+def test_d_fast_callers_mirrors_match_the_reference(world):
+    """--callers fast: this package's mirrors of backbone / voting / proposal / GridConv modules and compute_iou_labels
+    (dropin_callers/, SURVEY 8f n1 + n2) under the reference's VoteNet: same state dict, same indices, outputs within the
+    same bounds as the unchanged callers, and no cuDNN / cuBLAS convolution left in the step."""
+    ra = world["ra"]
+    fast = ra.load(ra.dropin_paths(fast_callers=True), name="b200-fast")
+    assert "dropin_callers" in fast.files["models.grid_conv_module"] and "baseline" in fast.files["models.votenet_iou_branch"]
+    net_f, cfg_f = ra.build_votenet(fast, "scannet", K, seed=1)
+    sd_f, sd_r = net_f.state_dict(), world["net_r"].state_dict()
+    assert sd_f.keys() == sd_r.keys() and all(torch.equal(sd_f[k], sd_r[k]) for k in sd_f)
+    from torch.profiler import ProfilerActivity, profile
+    with torch.no_grad():
+        ra.forward_with_iou_labels(fast, net_f, cfg_f, world["pc"], world["labels"])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ep_f = ra.forward_with_iou_labels(fast, net_f, cfg_f, world["pc"], world["labels"])
+            torch.cuda.synchronize()
+    names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    libs = [n for n in names if any(t in n.lower() for t in ("cudnn", "cutlass", "gemm", "implicit_convolve", "sm90", "sm100_xmma"))]
+    assert not libs, "library GEMM / convolution kernels in the fast-caller step: %s" % sorted(set(libs))[:5]
+    ep_r = world["ep_r"]
+    for k in ("sa1_inds", "sa2_inds", "fp2_inds", "seed_inds", "aggregated_vote_inds"):
+        assert torch.equal(ep_f[k], ep_r[k]), k
+    for k, tol in (("sa4_features", 1e-4), ("fp2_features", 2e-4), ("vote_xyz", 2e-4), ("vote_features", 2e-4)):
+        _every_element(ep_f[k], ep_r[k], k, atol=tol, rtol=tol)
+    for k, tol in (("center", 1e-3), ("size", 1e-3), ("iou_scores", 2e-3), ("iou_labels", 2e-3), ("objectness_scores", 2e-3)):
+        err = (ep_f[k].float() - ep_r[k].float()).abs()
+        frac = float((err <= tol + tol * ep_r[k].float().abs()).float().mean())
+        assert frac >= 0.995, (k, frac, float(err.max()))
+    assert torch.equal(ep_f["iou_objectness_label"], ep_r["iou_objectness_label"]) or \
+        float((ep_f["iou_objectness_label"] == ep_r["iou_objectness_label"]).float().mean()) > 0.995
+    # block-diagonal IoU labels on the REFERENCE's boxes == the diagonal blocks of its all-pairs matrix
+    pred, lab, cfg = ep_r["pred_bbox"], world["labels"], world["cfg_r"]
+    center = lab["center_label"].clone()
+    center[(1 - lab["box_label_mask"]).unsqueeze(-1).expand(-1, -1, 3).bool()] = -1000
+    gt = torch.cat([center, cfg.class2size_gpu(lab["size_class_label"], lab["size_residual_label"]),
+                    -cfg.class2angle_gpu(lab["heading_class_label"], lab["heading_residual_label"])[:, :, None]], 2)
+    blk = fast.iou.boxes_iou3d_batched(pred.contiguous(), gt.contiguous()).max(dim=2)[0]
+    _every_element(blk, ep_r["iou_labels"], "block-diagonal iou_labels", atol=1e-5, rtol=0)

@@ -73,6 +73,87 @@ def allreduce_gradients(model, average=True):
     return int(flat.numel())
 
 
+class GradientBuckets:
+    """The gradient exchange overlapped with the tail of backward.
+
+    Parameters are cut into `n_buckets` contiguous groups in REVERSE module order (backward reaches the heads first, the
+    backbone last).  A post-accumulate-grad hook counts the gradients of each group; when a group is complete its flat
+    bucket is all-reduced asynchronously (NCCL runs it on its own stream) while autograd keeps working on the earlier
+    layers.  finish() waits for the outstanding reductions, averages and scatters the results back.  A parameter that
+    received no gradient contributes zeros, so every rank reduces identical layouts (see allreduce_gradients)."""
+
+    def __init__(self, model, n_buckets=3, average=True):
+        self.average = average
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dtypes = {p.dtype for p in self.params}
+        if len(dtypes) > 1:
+            raise TypeError("GradientBuckets: a single parameter dtype is required, got %s" % sorted(map(str, dtypes)))
+        rev = list(reversed(self.params))
+        total = sum(p.numel() for p in rev)
+        self.buckets, cur, acc = [], [], 0
+        for p in rev:
+            cur.append(p)
+            acc += p.numel()
+            if acc >= total * (len(self.buckets) + 1) / max(n_buckets, 1) and len(self.buckets) < n_buckets - 1:
+                self.buckets.append(cur)
+                cur = []
+        if cur:
+            self.buckets.append(cur)
+        self.owner = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+        self.pending = [0] * len(self.buckets)
+        self.work = [None] * len(self.buckets)
+        self.flat = [None] * len(self.buckets)
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.begin()
+
+    def begin(self):
+        """Call before every backward."""
+        self.pending = [len(b) for b in self.buckets]
+        self.work = [None] * len(self.buckets)
+        self.flat = [None] * len(self.buckets)
+
+    def _launch(self, bi):
+        bucket = self.buckets[bi]
+        self.flat[bi] = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        if self.active:
+            self.work[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, async_op=True)
+
+    def _hook(self, p):
+        bi = self.owner[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def finish(self):
+        """After backward: reduce the groups whose hooks never completed (unused parameters), wait, write back.
+        Returns the number of elements reduced."""
+        n = 0
+        world = dist.get_world_size() if self.active else 1
+        for bi, bucket in enumerate(self.buckets):
+            if self.flat[bi] is None:
+                self._launch(bi)
+            if self.work[bi] is not None:
+                self.work[bi].wait()
+            flat = self.flat[bi]
+            if self.average and world > 1:
+                flat /= world
+            off = 0
+            for p in bucket:
+                k = p.numel()
+                if p.grad is None:
+                    p.grad = flat[off:off + k].view_as(p).clone()
+                else:
+                    p.grad.copy_(flat[off:off + k].view_as(p.grad))
+                off += k
+            n += off
+        return n
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 def broadcast_parameters(model, src=0):
     """Identical replicas at start-up (parameters and buffers), one flat broadcast."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -104,3 +104,60 @@ def test_flat_bucket_gradient_allreduce(tmp_path):
     assert got["n"] == sum(p.numel() for p in net.parameters())
     for a, b in zip(got["grads"], total):
         assert torch.allclose(a, b, atol=1e-6), (a - b).abs().max()
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = importlib.import_module("3dioumatch_b200.shard")
+    torch.manual_seed(7)
+    net = torch.nn.ModuleDict({"a": torch.nn.Linear(5, 7), "b": torch.nn.Linear(7, 3), "unused": torch.nn.Linear(3, 2),
+                               "rank1_only": torch.nn.Linear(3, 1)})
+    buckets = shard.GradientBuckets(net, n_buckets=3, average=True)
+    torch.manual_seed(rank)
+    x = torch.randn(4, 5)
+    for _ in range(2):                                     # two steps: begin() must re-arm the hooks
+        for p in net.parameters():
+            p.grad = None
+        buckets.begin()
+        y = net["b"](torch.relu(net["a"](x)))
+        loss = y.square().sum()
+        if rank == 1:                                      # a head only this rank's shard exercises
+            loss = loss + net["rank1_only"](y).sum()
+        loss.backward()
+        n = buckets.finish()
+    torch.save({"grads": {k: p.grad.clone() for k, p in net.named_parameters()}, "n": n, "x": x,
+                "state": {k: v.clone() for k, v in net.state_dict().items()}}, os.path.join(out_dir, "b%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_buckets_overlap_hooks_and_unused_parameters(tmp_path):
+    """GradientBuckets (hook-launched asynchronous bucket all-reduces): every rank ends with the MEAN gradient, parameters
+    without a gradient on some (or all) ranks contribute zeros instead of desynchronising the bucket layout."""
+    port = 29000 + ((os.getpid() + 13) % 2000)
+    mp.spawn(_bucket_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert r0["n"] == r1["n"] == sum(v.numel() for v in r0["state"].values())
+    for k in r0["grads"]:
+        assert torch.equal(r0["grads"][k], r1["grads"][k]), k          # identical on both ranks after the exchange
+    # single-process reference
+    ref = {}
+    for rank, rec in enumerate((r0, r1)):
+        net = torch.nn.ModuleDict({"a": torch.nn.Linear(5, 7), "b": torch.nn.Linear(7, 3), "unused": torch.nn.Linear(3, 2),
+                                   "rank1_only": torch.nn.Linear(3, 1)})
+        net.load_state_dict(rec["state"])
+        y = net["b"](torch.relu(net["a"](rec["x"])))
+        loss = y.square().sum()
+        if rank == 1:
+            loss = loss + net["rank1_only"](y).sum()
+        loss.backward()
+        for k, p in net.named_parameters():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            ref[k] = ref.get(k, 0) + g / 2
+    for k in ref:
+        assert torch.allclose(r0["grads"][k], ref[k], atol=1e-6), k
+    assert float(r0["grads"]["unused.weight"].abs().sum()) == 0.0

@@ -15,6 +15,12 @@ class MlpLayer(ctypes.Structure):
     _fields_ = [("cin", c_int), ("cout", c_int), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
 
 
+class BnLayer(ctypes.Structure):
+    """b200_bn_layer"""
+    _fields_ = [("cin", c_int), ("cout", c_int), ("weight", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/*.h
 PROTOTYPES = {
     "b200_abi_version": (c_int, []),
@@ -60,6 +66,16 @@ PROTOTYPES = {
     "b200pn2_row_mlp_forward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_int,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200pn2_transpose_cn": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "b200pn2_sa_train_saved_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(BnLayer), c_int]),
+    "b200pn2_sa_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(BnLayer), c_int,
+                                                    c_int]),
+    "b200pn2_sa_train_forward": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(BnLayer), c_float, c_float,
+                                         c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_sa_train_backward": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                          ctypes.POINTER(BnLayer), c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                          ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                          c_void_p, c_size_t, c_void_p]),
     "b200pn2_sa_tensor_work": (c_int, [ctypes.POINTER(ctypes.c_ulonglong), c_int]),
     "b200iou_boxes_overlap_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b200iou_boxes_iou_bev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

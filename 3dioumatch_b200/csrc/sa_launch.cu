@@ -236,6 +236,7 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
   p.out = c.out; p.out_pm = c.out_pm;
   p.rows_total = c.rows_total; p.rows_per_scene = c.rows_per_scene > 0 ? c.rows_per_scene : 1;
   p.ld = c.ld > 0 ? c.ld : c.C;
+  p.in_scale = c.in_scale; p.in_shift = c.in_shift; p.stats = c.stats;
   // 16-byte loads of whole 4-channel groups: aligned base and row stride; a ragged tail (C % 4) goes through scalar loads
   p.vec_gather = g.factor ? 1 : ((c.C >= 4 && (p.ld & 3) == 0 && (c.mode == 2 || (c.C & 3) == 0) &&
                                   ((((uintptr_t)c.feat_pm) & 15) == 0)) ? 1 : 0);

@@ -65,6 +65,12 @@ struct TcParams {
   const float *feat2_pm;
   int C2;
   int ld;  // mode 2: row stride of feat_pm in floats (>= C; rows padded to a multiple of 4 floats stay vector-loadable)
+  // training-mode layer passes (TRAIN kernels; sa_train.cu): input rows are the previous layer's raw conv output and
+  // become relu(in_scale * z + in_shift) on their way into the operand ring (BatchNorm with batch statistics + ReLU,
+  // pytorch_utils.py:42-61); the epilogue also emits per-tile column sums of the output and of its square,
+  // stats[((tile * 4 + row quarter) * 2 + {0: sum, 1: sum of squares}) * 256 + column]
+  const float *in_scale, *in_shift;
+  float *stats;
   TcLayer L[TC_MAXL];
 };
 
@@ -89,6 +95,8 @@ struct TcCall {
   const float *feat2_pm = nullptr;
   int C2 = 0;
   int ld = 0;  // mode 2: row stride (0: C)
+  const float *in_scale = nullptr, *in_shift = nullptr;  // training passes: affine + ReLU applied to the input rows
+  float *stats = nullptr;                                 // training passes: per-tile column sums (see TcParams)
   int rowout = 0, final_relu = 1, rows_total = 0, rows_per_scene = 0;
   float *out = nullptr, *out_pm = nullptr;
   int num_layers = 0;

@@ -128,6 +128,25 @@ __device__ __forceinline__ void transpose_max(float (&v)[32], int lane, int top_
 }
 
 
+// Same butterfly with addition over all 32 lanes: lane j ends with the sum over the warp's rows of column j (in v[0]).
+// The order of additions is fixed by the butterfly, so the result is deterministic.
+__device__ __forceinline__ void transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int n = 16 >> s;
+    const int off = 16 >> s;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float keep = upper ? v[i + n] : v[i];
+        const float send = upper ? v[i] : v[i + n];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+}
+
 // ---- compacted tiles: which 16-slot units of each centre hold distinct neighbours -----------------------------------
 // The reference's ball query pads a neighbour list shorter than nsample with copies of its first hit
 // (ball_query_gpu.cu:40-46), and max() over duplicated rows is the max over the distinct ones, so only the slots up
@@ -198,7 +217,10 @@ __device__ unsigned long long g_tcp_prof[48];
 // ROWOUT: the final epilogue stores every row's output (point-major and/or channel-major, optional ReLU) instead of the
 // max over nsample rows -- the per-point GEMM of a factorised first layer, the feature-propagation MLP and the 1x1-conv
 // heads (row MLPs).
-template <int MODE, int PRE, int ROWOUT>
+// TRAIN: one layer of a training-mode stack (plain rows in, raw conv rows out): affine + ReLU of the previous layer's
+// batch-statistics BatchNorm applied to the input rows in the producers, per-tile column sums of the output (the next
+// BatchNorm's statistics) in the epilogue.
+template <int MODE, int PRE, int ROWOUT, int TRAIN = 0>
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -208,6 +230,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   float *s_shift = s_scale + TC_MAXL * 256;
   float *s_partial = s_shift + TC_MAXL * 256;                                // [2][4][256] per-warp maxima (nsample > 32)
   float *s_wx = s_partial + 2 * 4 * 256;                                     // [3][128] scale1 * W1x (factorised layer 1)
+  float *s_in = s_wx + 3 * 128;                                              // [2][256] input affine (TRAIN)
 
   __shared__ uint64_t full_a[TP_ASTAGES], empty_a[TP_ASTAGES], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
   __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free, tq_full[TP_TQ], tq_empty[TP_TQ];
@@ -246,6 +269,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     s_shift[e] = c < p.L[l].cout ? p.L[l].shift[c] : 0.f;
   }
   for (int e = tid; e < 3 * 128; e += TP_THREADS) s_wx[e] = PRE ? p.wx[e] : 0.f;
+  if (TRAIN) {
+    for (int e = tid; e < 256; e += TP_THREADS) {
+      s_in[e] = (p.in_scale && e < p.C) ? p.in_scale[e] : 1.f;
+      s_in[256 + e] = (p.in_shift && e < p.C) ? p.in_shift[e] : 0.f;
+    }
+  }
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -544,6 +573,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].w = fmaxf(__fmaf_rn(w2.w, rel[2], __fmaf_rn(w1.w, rel[1], __fmaf_rn(w0.w, rel[0], v[c].w))), 0.f);
           }
         }
+        if (TRAIN && p.in_scale) {
+          // the previous layer's BatchNorm (batch statistics folded to an affine) + ReLU; rows past the end stay zero
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = kb * 32 + c * 4;
+            const float4 s4 = *reinterpret_cast<const float4 *>(s_in + ch);
+            const float4 h4 = *reinterpret_cast<const float4 *>(s_in + 256 + ch);
+            v[c].x = valid ? fmaxf(fmaf(v[c].x, s4.x, h4.x), 0.f) : 0.f;
+            v[c].y = valid ? fmaxf(fmaf(v[c].y, s4.y, h4.y), 0.f) : 0.f;
+            v[c].z = valid ? fmaxf(fmaf(v[c].z, s4.z, h4.z), 0.f) : 0.f;
+            v[c].w = valid ? fmaxf(fmaf(v[c].w, s4.w, h4.w), 0.f) : 0.f;
+          }
+        }
         TPW(9, &empty_a[sa], pa ^ 1u);
         uint8_t *a_hi = R1 + sa * 2 * TC_KB_BYTES, *a_lo = a_hi + TC_KB_BYTES;
 #pragma unroll
@@ -686,6 +728,22 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                   const int gg = row / ns;
                   rvalid = gg < g_here;
                   grow = ((size_t)b * p.M + m0 + gg) * ns + (row - gg * ns);
+                }
+                if (TRAIN && p.stats) {
+                  // column sums over this warp's 32 rows of the raw output and of its square (rows past the end are exact
+                  // zeros: zero operand rows, unit scale, zero shift); butterfly transpose-add: lane j ends with column j
+                  float sv[32], sq[32];
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float x = rvalid ? (__uint_as_float(r[i]) + __uint_as_float(r2[i])) : 0.f;
+                    sv[i] = x;
+                    sq[i] = x * x;
+                  }
+                  transpose_sum(sv, lane);
+                  transpose_sum(sq, lane);
+                  float *dst = p.stats + ((size_t)(t * 4 + (warp & 3)) * 2) * 256 + c0 + lane;
+                  dst[0] = sv[0];
+                  dst[256] = sq[0];
                 }
                 if (rvalid) {
                   float o[32];
@@ -840,11 +898,11 @@ int sa_tcp_units_from_idx(int B, int M, int nsample, const int32_t *idx, int *un
   return 0;
 }
 
-template <int MODE, int PRE, int ROWOUT>
+template <int MODE, int PRE, int ROWOUT, int TRAIN = 0>
 static int launch_variant(const TcParams &p, int grid, size_t smem, cudaStream_t stream) {
   static DynSmemOptIn optin;  // one per kernel instantiation, per device inside
-  B200_CUDA_OK(optin.ensure(sa_tcp_kernel<MODE, PRE, ROWOUT>, smem));
-  sa_tcp_kernel<MODE, PRE, ROWOUT><<<grid, TP_THREADS, smem, stream>>>(p);
+  B200_CUDA_OK(optin.ensure(sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN>, smem));
+  sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN><<<grid, TP_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_tcp_kernel");
   return 0;
 }
@@ -866,7 +924,8 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   p.total_tiles = p.mode == 2 ? ceil_div(p.rows_total, TC_ROWS) : p.B * p.tiles_per_scene;
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
-  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float);
+  const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float) +
+                       2 * 256 * sizeof(float);
   p.a_stages = (force_astages >= 2 && force_astages <= TP_ASTAGES) ? force_astages : 3;
   p.r1_bytes = p.a_stages * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
@@ -879,6 +938,10 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (p.nl == 1 && 2 * grid < p.total_tiles) grid = ceil_div(p.total_tiles, 2);  // at most two tiles per CTA (see publish())
   if (grid <= 0) return 0;
+  if (p.in_scale || p.stats) {
+    B200_CHECK_ARG(p.mode == 2 && p.rowout && !p.pre && p.nl == 1, "training pass: one plain-row layer per launch");
+    return launch_variant<2, 0, 1, 1>(p, grid, smem, stream);
+  }
   const int key = p.mode * 4 + (p.pre ? 2 : 0) + (p.rowout ? 1 : 0);
   switch (key) {
     case 0: return launch_variant<0, 0, 0>(p, grid, smem, stream);   // ball-query lists -> MLP -> max

@@ -359,3 +359,89 @@ def split_row_groups(layers):
     if cur:
         groups.append(cur)
     return groups
+
+
+# ---- training-mode fused SA (include/b200_pointnet2.h: b200pn2_sa_train_forward / _backward) -------------------------
+
+def _bn_array(layers):
+    """[(weight (cout,cin), gamma, beta, running_mean or None, running_var or None)] -> b200_bn_layer[]"""
+    arr = (cabi.BnLayer * len(layers))()
+    keep = []
+    for i, (w, g, b, rm, rv) in enumerate(layers):
+        w2 = w.reshape(w.size(0), -1)
+        for t, nm in ((w2, "weight"), (g, "gamma"), (b, "beta")):
+            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
+        keep.append(w2)
+        arr[i].cin, arr[i].cout = w2.size(1), w2.size(0)
+        arr[i].weight, arr[i].gamma, arr[i].beta = w2.data_ptr(), g.data_ptr(), b.data_ptr()
+        arr[i].running_mean = rm.data_ptr() if rm is not None else None
+        arr[i].running_var = rv.data_ptr() if rv is not None else None
+    return arr, keep
+
+
+def sa_train_supported(C, use_xyz, layers, rows_mode=False):
+    arr, keep = _bn_array(layers)
+    return int(_L().b200pn2_sa_train_saved_bytes(1, 1, 1, int(C), int(bool(use_xyz)), len(layers), arr, int(rows_mode))) > 0
+
+
+def sa_train_forward(xyz, features_pm, new_xyz, idx, radius, nsample, layers, eps, momentum, use_xyz=True,
+                     normalize_xyz=False, x_rows=None, groups=None):
+    """Training-mode SA MLP forward.  Gather mode: xyz (B,N,3), features_pm (B,N,C) or None, new_xyz (B,M,3), idx
+    (B,M,nsample).  Rows mode: x_rows (G*nsample, C) with groups = (B, M).  layers as for _bn_array (running statistics
+    are updated in place).  Returns (out (B,cout,M), saved uint8 tensor)."""
+    arr, keep = _bn_array(layers)
+    if x_rows is not None:
+        _contig(x_rows, "x_rows"); _is_float(x_rows, "x_rows"); _cuda(x_rows, None)
+        B, M = groups
+        N, C, dev = 0, x_rows.size(1), x_rows.device
+        _chk(x_rows.size(0) == B * M * int(nsample), "x_rows must hold B*M*nsample rows")
+    else:
+        for t, nm in ((xyz, "xyz"), (new_xyz, "new_xyz")):
+            _contig(t, nm); _is_float(t, nm); _cuda(t, nm)
+        _contig(idx, "idx"); _is_int(idx, "idx"); _cuda(idx, "idx")
+        B, N, M, dev = xyz.size(0), xyz.size(1), new_xyz.size(1), xyz.device
+        C = 0
+        if features_pm is not None:
+            _contig(features_pm, "features_pm"); _is_float(features_pm, "features_pm"); _cuda(features_pm, "features_pm")
+            C = features_pm.size(2)
+    rows_mode = int(x_rows is not None)
+    cout = layers[-1][0].size(0)
+    with torch.cuda.device(dev):
+        nsaved = int(_L().b200pn2_sa_train_saved_bytes(B, M, int(nsample), C, int(bool(use_xyz)), len(layers), arr, rows_mode))
+        _chk(nsaved > 0, "sa_train_forward: stack not supported by the fused training kernels")
+        nws = int(_L().b200pn2_sa_train_workspace_bytes(B, M, int(nsample), C, int(bool(use_xyz)), len(layers), arr, rows_mode, 0))
+        saved = torch.empty((nsaved,), dtype=torch.uint8, device=dev)
+        ws = torch.empty((max(nws, 1),), dtype=torch.uint8, device=dev)
+        out = torch.empty((B, cout, M), dtype=torch.float32, device=dev)
+        cabi.check(_L().b200pn2_sa_train_forward(B, N, M, C, float(radius), int(nsample), int(bool(use_xyz)),
+                                                 int(bool(normalize_xyz)), _p(xyz), _p(features_pm), _p(new_xyz), _p(idx),
+                                                 _p(x_rows), len(layers), arr, float(eps), float(momentum), _p(out),
+                                                 _p(saved), nsaved, _p(ws), nws, stream_ptr()), "sa_train_forward")
+    return out, saved
+
+
+def sa_train_backward(grad_out, saved, idx, nsample, layers, B, N, M, C, use_xyz=True, x_rows=None, want_input_grad=True):
+    """Returns (grad_features (B,C,N) or grad_rows or None, [grad_weight], [grad_gamma], [grad_beta])."""
+    arr, keep = _bn_array(layers)
+    _contig(grad_out, "grad_out"); _is_float(grad_out, "grad_out"); _cuda(grad_out, None)
+    dev = grad_out.device
+    rows_mode = int(x_rows is not None)
+    L = len(layers)
+    gw = [torch.empty_like(l[0].reshape(l[0].size(0), -1)) for l in layers]
+    gg = [torch.empty_like(l[1]) for l in layers]
+    gb = [torch.empty_like(l[2]) for l in layers]
+    pw = (ctypes.c_void_p * L)(*[t.data_ptr() for t in gw])
+    pg = (ctypes.c_void_p * L)(*[t.data_ptr() for t in gg])
+    pb = (ctypes.c_void_p * L)(*[t.data_ptr() for t in gb])
+    gin = None
+    if want_input_grad and C > 0:
+        gin = torch.empty((x_rows.size(0), C) if rows_mode else (B, C, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nws = int(_L().b200pn2_sa_train_workspace_bytes(B, M, int(nsample), C, int(bool(use_xyz)), L, arr, rows_mode, 1))
+        ws = torch.empty((max(nws, 1),), dtype=torch.uint8, device=dev)
+        cabi.check(_L().b200pn2_sa_train_backward(B, N, M, C, int(nsample), int(bool(use_xyz)), _p(idx), _p(x_rows), L, arr,
+                                                  _p(grad_out), _p(saved), saved.numel(),
+                                                  _p(gin) if (gin is not None and not rows_mode) else ctypes.c_void_p(0),
+                                                  _p(gin) if (gin is not None and rows_mode) else ctypes.c_void_p(0),
+                                                  pw, pg, pb, _p(ws), nws, stream_ptr()), "sa_train_backward")
+    return gin, gw, gg, gb

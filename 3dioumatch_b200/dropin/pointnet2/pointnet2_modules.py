@@ -64,6 +64,86 @@ def _fused_stage(grouper, layers, xyz, new_xyz, features, features_pm=None, want
     return out, out_pm
 
 
+class _FusedTrainSA(torch.autograd.Function):
+    """group -> [conv1x1 -> BatchNorm2d(batch statistics) -> ReLU] x L -> max over nsample, forward and backward on the fused
+    training kernels (csrc/sa_train.cu; SURVEY 8f row n4).  Differentiable w.r.t. features, conv weights, BN gamma / beta;
+    coordinates are constants.  Running statistics are updated in place by the forward (torch's momentum rule)."""
+
+    @staticmethod
+    def forward(ctx, features, xyz, new_xyz, idx, cfg, *params):
+        radius, nsample, use_xyz, normalize, eps, momentum, running = cfg
+        L = len(params) // 3
+        layers = [(params[3 * i].detach(), params[3 * i + 1].detach(), params[3 * i + 2].detach(), running[i][0], running[i][1])
+                  for i in range(L)]
+        fpm = _ext.transpose_cn(features.detach().contiguous()) if features is not None else None
+        out, saved = _ext.sa_train_forward(xyz, fpm, new_xyz, idx, radius, nsample, layers, eps, momentum, use_xyz=use_xyz,
+                                           normalize_xyz=normalize)
+        ctx.save_for_backward(saved, idx, *[p.detach() for p in params])
+        ctx.meta = (xyz.size(0), xyz.size(1), new_xyz.size(1), features.size(1) if features is not None else 0, nsample, use_xyz,
+                    features is not None and features.requires_grad, [tuple(p.shape) for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved, idx = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        params = ctx.saved_tensors[2:]
+        B, N, M, C, nsample, use_xyz, want_feat, shapes = ctx.meta
+        L = len(params) // 3
+        layers = [(params[3 * i], params[3 * i + 1], params[3 * i + 2], None, None) for i in range(L)]
+        gin, gw, gg, gb = _ext.sa_train_backward(grad_out.contiguous(), saved, idx, nsample, layers, B, N, M, C, use_xyz=use_xyz,
+                                                 want_input_grad=want_feat)
+        grads = []
+        for i in range(L):
+            grads += [gw[i].view(shapes[3 * i]), gg[i], gb[i]]
+        return (gin if want_feat else None, None, None, None, None, *grads)
+
+
+def _train_fusable(grouper, mlp, xyz, features, pooling="max"):
+    """[(conv, bn)] when the stage can run on the fused training kernels: every block conv1x1(bias=False) -> BatchNorm2d in
+    training mode -> ReLU, max pooling, constant coordinates, one (eps, momentum) for the stack."""
+    if os.environ.get("B200_SA_TRAIN_FUSED", "1") == "0" or pooling != "max" or not xyz.is_cuda or xyz.requires_grad:
+        return None
+    if not isinstance(grouper, pointnet2_utils.QueryAndGroup) or grouper.sample_uniformly:
+        return None
+    pairs = []
+    for block in mlp.children():
+        conv = bn = act = None
+        for key, mod in block.named_children():
+            if key.endswith("conv"):
+                conv = mod
+            elif key.endswith("bn"):
+                bn = next(iter(mod.children()))
+            elif key.endswith("activation"):
+                act = mod
+        if conv is None or bn is None or not isinstance(act, nn.ReLU) or conv.bias is not None or not bn.training:
+            return None
+        if tuple(conv.kernel_size) != (1, 1) or not bn.affine or not bn.track_running_stats or bn.momentum is None:
+            return None
+        pairs.append((conv, bn))
+    if not pairs or len({(bn.eps, bn.momentum) for _, bn in pairs}) != 1:
+        return None
+    C = features.size(1) if features is not None else 0
+    probe = [(c.weight, b.weight, b.bias, None, None) for c, b in pairs]
+    if not _ext.sa_train_supported(C, grouper.use_xyz, probe):
+        return None
+    return pairs
+
+
+def _fused_train_stage(grouper, pairs, xyz, new_xyz, features):
+    idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+    bn0 = pairs[0][1]
+    cfg = (grouper.radius, grouper.nsample, grouper.use_xyz, grouper.normalize_xyz, bn0.eps, bn0.momentum,
+           [(bn.running_mean, bn.running_var) for _, bn in pairs])
+    params = []
+    for conv, bn in pairs:
+        params += [conv.weight, bn.weight, bn.bias]
+    out = _FusedTrainSA.apply(features, xyz, new_xyz, idx, cfg, *params)
+    with torch.no_grad():
+        for _, bn in pairs:
+            bn.num_batches_tracked += 1
+    return out
+
+
 def _pool(new_features, pooling, grouped_xyz=None, sigma=None, nsample=None):
     if pooling == "max":
         out = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
@@ -177,6 +257,10 @@ class PointnetSAModuleVotes(nn.Module):
         if layers is not None:
             new_features, _ = _fused_stage(self.grouper, layers, xyz, new_xyz, features, mlp=self.mlp_module)
             return new_xyz, new_features, inds
+        if new_xyz is not None and not self.ret_unique_cnt:
+            pairs = _train_fusable(self.grouper, self.mlp_module, xyz, features, self.pooling)
+            if pairs is not None:
+                return new_xyz, _fused_train_stage(self.grouper, pairs, xyz, new_xyz, features), inds
 
         grouped = self.grouper(xyz, new_xyz, features)
         if self.ret_unique_cnt:

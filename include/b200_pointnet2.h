@@ -210,6 +210,42 @@ int b200pn2_transpose_cn(int B, int C, int N, const float *in_cm, float *out_pm,
  * FLOP/s of the roofline.                                                                                          */
 int b200pn2_sa_tensor_work(unsigned long long *mma_n_columns, int reset);
 
+/* ---- training-mode set-abstraction MLP: conv1x1 -> BatchNorm2d on BATCH statistics -> ReLU per layer,
+ * max over nsample, and the backward of all of it (pointnet2/pytorch_utils.py:14-61,70-123; pointnet2_modules.py:256-262;
+ * input-feature gradient = group_points_grad, group_points_gpu.cu:48-68).  Layer at a time; only the raw conv outputs of
+ * each layer are kept for backward (`saved`), BatchNorm / ReLU / max-pool are fused into the loads and stores of the GEMMs.
+ *   weight (cout, cin), gamma / beta (cout); running_mean / running_var (cout) are updated in place with torch's rule
+ *   (momentum, unbiased variance) or may be NULL.  Widths: multiples of 4, <= 256; cin <= 320; 1..4 layers.
+ *   Gather mode  (x_rows == NULL): rows = grouped [rel xyz * 1/r (3) | features (C)] of idx (B,M,nsample), features_pm
+ *                (B,N,C) point-major; backward returns grad_features (B,C,N) (xyz is treated as a constant).
+ *   Rows mode    (x_rows != NULL): the stack on given rows (B*M*nsample, C), C a multiple of 4; backward returns grad_rows.
+ *   out (B, cout_last, M).  `saved` >= b200pn2_sa_train_saved_bytes(...), `workspace` >= ..._workspace_bytes(..., backward).
+ * Weight / gamma / beta gradients and the statistics are reduced in a fixed order (bit-reproducible).               */
+typedef struct {
+  int cin;
+  int cout;
+  const float *weight;
+  const float *gamma;
+  const float *beta;
+  float *running_mean;
+  float *running_var;
+} b200_bn_layer;
+
+size_t b200pn2_sa_train_saved_bytes(int B, int M, int nsample, int C, int use_xyz, int num_layers,
+                                    const b200_bn_layer *layers, int rows_mode);
+size_t b200pn2_sa_train_workspace_bytes(int B, int M, int nsample, int C, int use_xyz, int num_layers,
+                                        const b200_bn_layer *layers, int rows_mode, int backward);
+int b200pn2_sa_train_forward(int B, int N, int M, int C, float radius, int nsample, int use_xyz, int normalize_xyz,
+                             const float *xyz, const float *features_pm, const float *new_xyz, const int32_t *idx,
+                             const float *x_rows, int num_layers, const b200_bn_layer *layers, float eps, float momentum,
+                             float *out, void *saved, size_t saved_bytes, void *workspace, size_t workspace_bytes,
+                             b200_stream_t stream);
+int b200pn2_sa_train_backward(int B, int N, int M, int C, int nsample, int use_xyz, const int32_t *idx,
+                              const float *x_rows, int num_layers, const b200_bn_layer *layers, const float *grad_out,
+                              const void *saved, size_t saved_bytes, float *grad_features, float *grad_rows,
+                              float *const *grad_weight, float *const *grad_gamma, float *const *grad_beta,
+                              void *workspace, size_t workspace_bytes, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

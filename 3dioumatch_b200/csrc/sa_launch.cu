@@ -27,6 +27,7 @@ struct PackParams {
   const float *w[TC_MAXL];
   int cin[TC_MAXL], cout[TC_MAXL], nkb[TC_MAXL], nhalf[TC_MAXL], rows[TC_MAXL];
   int ld[TC_MAXL];  // row stride of the source matrix (== cin unless a column range of a wider matrix is packed)
+  int transposed;   // layer 0: element (n, k) of the packed matrix is source[k * ld + n] (backward passes: W^T)
   size_t off[TC_MAXL];
   // grid row nl: for a factorised first layer, wx[k][c] = scale1[c] * W1[c][k] for its three relative-xyz input
   // columns (zero without xyz channels)
@@ -60,7 +61,9 @@ __global__ void __launch_bounds__(256) tc_pack_weights_kernel(PackParams p, uint
       const int k = kb * 32 + chunk * 4 + e;
       int src = k;
       if (l == 0 && p.perm_c >= 0) src = k < p.perm_c ? 3 + k : k - p.perm_c;
-      v[e] = (n < p.cout[l] && k < p.cin[l]) ? p.w[l][(size_t)n * p.ld[l] + src] : 0.f;
+      v[e] = (n < p.cout[l] && k < p.cin[l])
+                 ? ((l == 0 && p.transposed) ? p.w[l][(size_t)src * p.ld[l] + n] : p.w[l][(size_t)n * p.ld[l] + src])
+                 : 0.f;
       tc::split_tf32(v[e], hi[e], lo[e]);
     }
     const size_t stage_bytes = (size_t)rows * 256;  // hi rows | lo rows, 128 B each
@@ -158,8 +161,9 @@ bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200
 
 // ---- plan: the packed weights of a stack in device memory the CALLER owns (one per module, rebuilt when weights change) --
 static int pack_into(const StackGeom &g, int C_feat, int use_xyz, int perm_xyz_last, const b200_mlp_layer *layers,
-                     uint8_t *plan, cudaStream_t stream) {
+                     uint8_t *plan, cudaStream_t stream, int w_transposed = 0, int w_ld = 0) {
   PackParams pk = {};
+  pk.transposed = w_transposed;
   pk.nl = g.nl;
   // the kernel's layer-1 operand is [features (C) | rel xyz (3)] while the reference concatenates [xyz | features]
   // (pointnet2_utils.py:358-360): permute the first layer's columns while packing
@@ -171,6 +175,7 @@ static int pack_into(const StackGeom &g, int C_feat, int use_xyz, int perm_xyz_l
     pk.ld[i] = L.cin;
     pk.cout[i] = L.cout;
     pk.nkb[i] = g.nkb[i]; pk.nhalf[i] = g.nhalf[i]; pk.rows[i] = g.rows[i]; pk.off[i] = g.off[i];
+    if (i == 0 && w_ld > 0) pk.ld[i] = w_ld;
   }
   pk.wx = reinterpret_cast<float *>(plan + g.wx_off);
   if (g.factor) {
@@ -219,7 +224,7 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
   B200_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
   const uint8_t *plan = (const uint8_t *)plan_in;
   if (!plan) {
-    const int rc = pack_into(g, C_stack, c.use_xyz, c.mode != 2, c.layers, sc + plan_off, stream);
+    const int rc = pack_into(g, C_stack, c.use_xyz, c.mode != 2, c.layers, sc + plan_off, stream, c.w_transposed, c.w_ld);
     if (rc) return rc;
     plan = sc + plan_off;
   }
@@ -237,6 +242,9 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
   p.rows_total = c.rows_total; p.rows_per_scene = c.rows_per_scene > 0 ? c.rows_per_scene : 1;
   p.ld = c.ld > 0 ? c.ld : c.C;
   p.in_scale = c.in_scale; p.in_shift = c.in_shift; p.stats = c.stats;
+  p.train_in = c.train_in; p.train_out = c.train_out; p.pool_ns = c.pool_ns > 0 ? c.pool_ns : 1;
+  p.g_rows = c.g_rows; p.gout_pm = c.gout_pm; p.dz_b = c.dz_b; p.dz_c = c.dz_c; p.arg_pm = c.arg_pm;
+  p.zprev = c.zprev; p.out_scale = c.out_scale; p.out_shift = c.out_shift; p.out_mean = c.out_mean; p.out_invstd = c.out_invstd;
   // 16-byte loads of whole 4-channel groups: aligned base and row stride; a ragged tail (C % 4) goes through scalar loads
   p.vec_gather = g.factor ? 1 : ((c.C >= 4 && (p.ld & 3) == 0 && (c.mode == 2 || (c.C & 3) == 0) &&
                                   ((((uintptr_t)c.feat_pm) & 15) == 0)) ? 1 : 0);

@@ -71,6 +71,16 @@ struct TcParams {
   // stats[((tile * 4 + row quarter) * 2 + {0: sum, 1: sum of squares}) * 256 + column]
   const float *in_scale, *in_shift;
   float *stats;
+  // backward passes of the same kernels (da = dz W): the input rows are dz_l, built in the producers from the saved raw
+  // conv output z (feat_pm) and the upstream gradient,   dz = in_scale * g + dz_b + dz_c * z   (BatchNorm backward folded to
+  // three per-channel coefficients);  train_in 2: g = g_rows (R, ld);  train_in 3 (top layer): g = grad_out of the pooled
+  // output where this row is its centre's arg-max slot and the pooled value is positive (in_shift = the layer's shift).
+  // train_out 1: the epilogue multiplies by the ReLU mask of the layer below (zprev, out_scale, out_shift) and the column
+  // sums become sum g, sum g * xhat (out_mean, out_invstd) -- the next BatchNorm backward's statistics.
+  int train_in, train_out, pool_ns;
+  const float *g_rows, *gout_pm, *dz_b, *dz_c;
+  const int32_t *arg_pm;
+  const float *zprev, *out_scale, *out_shift, *out_mean, *out_invstd;
   TcLayer L[TC_MAXL];
 };
 
@@ -97,6 +107,11 @@ struct TcCall {
   int ld = 0;  // mode 2: row stride (0: C)
   const float *in_scale = nullptr, *in_shift = nullptr;  // training passes: affine + ReLU applied to the input rows
   float *stats = nullptr;                                 // training passes: per-tile column sums (see TcParams)
+  int train_in = 0, train_out = 0, pool_ns = 1;           // backward passes (see TcParams)
+  const float *g_rows = nullptr, *gout_pm = nullptr, *dz_b = nullptr, *dz_c = nullptr;
+  const int32_t *arg_pm = nullptr;
+  const float *zprev = nullptr, *out_scale = nullptr, *out_shift = nullptr, *out_mean = nullptr, *out_invstd = nullptr;
+  int w_transposed = 0, w_ld = 0;  // single-layer calls: the weight matrix is read transposed (cin x cout view of a (cout, w_ld) matrix)
   int rowout = 0, final_relu = 1, rows_total = 0, rows_per_scene = 0;
   float *out = nullptr, *out_pm = nullptr;
   int num_layers = 0;

@@ -42,44 +42,6 @@ constexpr int TP_TQ = 4;        // depth of the tile-id ring
 constexpr int TP_MAXSLOTS = 8;  // weight ring slots (p.nslots = 3..8)
 constexpr int TP_ASTAGES = 4;   // layer-1 operand ring: at most this many stages (A_hi | A_lo of one k-block each)
 
-// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
-  const uint32_t addr = tc::smem_addr(bar);
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (spin == 256) t0 = clock64();
-    if (spin > 256 && (spin & 255u) == 0u && clock64() - t0 > 6000000000LL) {
-      printf("[b200] sa_tcp_kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, addr, parity);
-      __trap();
-    }
-  }
-}
-
-// one leader lane of a converged warp (the same lane every time: tcgen05.commit tracks the issuing thread)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (128 lanes x 8 columns of TF32) is read from tensor memory
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -230,10 +192,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   float *s_shift = s_scale + TC_MAXL * 256;
   float *s_partial = s_shift + TC_MAXL * 256;                                // [2][4][256] per-warp maxima (nsample > 32)
   float *s_wx = s_partial + 2 * 4 * 256;                                     // [3][128] scale1 * W1x (factorised layer 1)
-  float *s_in = s_wx + 3 * 128;                                              // [2][256] input affine (TRAIN)
+  float *s_in = s_wx + 3 * 128;                                              // [4][256] input coefficients, [4][256] output (TRAIN)
+  float *s_out = s_in + 4 * 256;
 
   __shared__ uint64_t full_a[TP_ASTAGES], empty_a[TP_ASTAGES], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
-  __shared__ uint64_t accum_full, x_ready, accum_half[2], d_free, tq_full[TP_TQ], tq_empty[TP_TQ];
+  // accum_half is indexed by (accumulator region, half): a barrier advances once per TWO tiles, and the MMA warp may not
+  // start a tile before every epilogue thread has finished the tile that used its region (acc_free / the hidden hand-off),
+  // so no waiter can be lapped (a per-tile barrier could complete two phases -- K = 4 layers take ~200 cycles per tile --
+  // before a slow epilogue warp polled the first: its parity wait would then block forever)
+  __shared__ uint64_t accum_full, x_ready, accum_half[4], d_free, acc_free[2], tq_full[TP_TQ], tq_empty[TP_TQ];
   __shared__ int tq_tile[TP_TQ];
   __shared__ uint32_t tmem_base_s;
 
@@ -248,9 +215,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       tc::mbar_init(&full_a[s], 128);
       tc::mbar_init(&empty_a[s], 1);
     }
-    tc::mbar_init(&accum_half[0], 1);
-    tc::mbar_init(&accum_half[1], 1);
+    for (int s = 0; s < 4; ++s) tc::mbar_init(&accum_half[s], 1);
     tc::mbar_init(&d_free, TP_EPI);
+    tc::mbar_init(&acc_free[0], TP_EPI);
+    tc::mbar_init(&acc_free[1], TP_EPI);
     for (int s = 0; s < TP_MAXSLOTS; ++s) {
       tc::mbar_init(&full_w[s], 1);
       tc::mbar_init(&empty_w[s], 1);
@@ -270,9 +238,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   }
   for (int e = tid; e < 3 * 128; e += TP_THREADS) s_wx[e] = PRE ? p.wx[e] : 0.f;
   if (TRAIN) {
+    const int co = p.L[0].cout;
     for (int e = tid; e < 256; e += TP_THREADS) {
       s_in[e] = (p.in_scale && e < p.C) ? p.in_scale[e] : 1.f;
       s_in[256 + e] = (p.in_shift && e < p.C) ? p.in_shift[e] : 0.f;
+      s_in[512 + e] = (p.dz_b && e < p.C) ? p.dz_b[e] : 0.f;
+      s_in[768 + e] = (p.dz_c && e < p.C) ? p.dz_c[e] : 0.f;
+      s_out[e] = (p.out_scale && e < co) ? p.out_scale[e] : 0.f;
+      s_out[256 + e] = (p.out_shift && e < co) ? p.out_shift[e] : 0.f;
+      s_out[512 + e] = (p.out_mean && e < co) ? p.out_mean[e] : 0.f;
+      s_out[768 + e] = (p.out_invstd && e < co) ? p.out_invstd[e] : 0.f;
     }
   }
   tc::tc_fence_before_sync();
@@ -314,12 +289,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       TPW(0, &tq_empty[slot], (uint32_t)(((n_pub / TP_TQ) & 1) ^ 1));
       int t = 0;
       if (lane == 0) {
-        if (nl == 1 && n_pub >= 2) {
-          // single-layer stack: a CTA takes at most two tiles, one per TMEM accumulator region.  A third would
-          // reuse the first one's region, and with one layer there is no hidden hand-off that orders its MMAs after
-          // that tile's epilogue (the launcher sizes the grid so that two per CTA cover every tile).
-          t = -1;
-        } else {
+        {
           t = atomicAdd(p.tile_counter, 1);
           if (t >= total_tiles) t = -1;
         }
@@ -362,6 +332,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       const uint32_t d_small = d_big + 128u;
       const uint32_t x_hi = tmem_d + ((tl & 1u) ? 0u : 256u);   // this tile's activation region (A operand, layers >= 2)
       const uint32_t x_lo = x_hi + 128u;
+      if (nl == 1 && tl >= 2u) {
+        // single-layer stack: no hidden hand-off orders this tile's MMAs after the epilogue of the tile that used this
+        // accumulator region two tiles ago -- wait for that epilogue's last TMEM read explicitly
+        TPW(4, &acc_free[tl & 1u], ((tl >> 1) - 1u) & 1u);
+        tc::tc_fence_after_sync();
+      }
       for (int l = 0; l < nl; ++l) {
         const bool last = l == nl - 1;
         if (l > 0) {
@@ -435,7 +411,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             if (sw == (uint32_t)nslots) { sw = 0; pw ^= 1u; }
           }
           if (last) {
-            if (elect_one()) tc::mma_commit(&accum_half[h]);
+            if (elect_one()) tc::mma_commit(&accum_half[(tl & 1u) * 2u + h]);
             __syncwarp();
           }
         }
@@ -517,7 +493,56 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
         rel[2] = __fmul_rn(__fsub_rn(q[2], ctr[2]), p.inv_r);
       }
       // layer-1 A operand: [features (C) | rel xyz (3) | 0 ...]
+      // TRAIN backward: the row's upstream gradient (dense rows, or the pooled gradient of the row's centre)
+      const float *g_row = nullptr, *go_row = nullptr;
+      const int32_t *arg_row = nullptr;
+      int my_slot = 0;
+      if (TRAIN && valid && p.train_in == 2) g_row = p.g_rows + ((size_t)t * TC_ROWS + row) * p.ld;
+      if (TRAIN && valid && p.train_in == 3) {
+        const long long rr = (long long)t * TC_ROWS + row, grp = rr / p.pool_ns;
+        my_slot = (int)(rr - grp * p.pool_ns);
+        go_row = p.gout_pm + grp * C;
+        arg_row = p.arg_pm + grp * C;
+      }
       auto load_kb = [&](int kb, float4 (&v)[8]) {
+        if (TRAIN && p.train_in >= 2) {
+          // dz = in_scale * g + dz_b + dz_c * z  (all loads of the k-block first, then the arithmetic)
+          float4 zv[8], gv[8];
+          int4 av[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = kb * 32 + c * 4;
+            const bool in = valid && ch + 3 < C;
+            zv[c] = in ? __ldg(reinterpret_cast<const float4 *>(frow + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.train_in == 2) {
+              gv[c] = in ? __ldg(reinterpret_cast<const float4 *>(g_row + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              gv[c] = in ? __ldg(reinterpret_cast<const float4 *>(go_row + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              av[c] = in ? __ldg(reinterpret_cast<const int4 *>(arg_row + ch)) : make_int4(-1, -1, -1, -1);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = kb * 32 + c * 4;
+            const bool in = valid && ch + 3 < C;
+            const float4 a4 = *reinterpret_cast<const float4 *>(s_in + ch);
+            const float4 h4 = *reinterpret_cast<const float4 *>(s_in + 256 + ch);
+            const float4 b4 = *reinterpret_cast<const float4 *>(s_in + 512 + ch);
+            const float4 c4 = *reinterpret_cast<const float4 *>(s_in + 768 + ch);
+            float4 g = gv[c];
+            if (p.train_in == 3) {
+              g.x = (av[c].x == my_slot && fmaf(zv[c].x, a4.x, h4.x) > 0.f) ? g.x : 0.f;
+              g.y = (av[c].y == my_slot && fmaf(zv[c].y, a4.y, h4.y) > 0.f) ? g.y : 0.f;
+              g.z = (av[c].z == my_slot && fmaf(zv[c].z, a4.z, h4.z) > 0.f) ? g.z : 0.f;
+              g.w = (av[c].w == my_slot && fmaf(zv[c].w, a4.w, h4.w) > 0.f) ? g.w : 0.f;
+            }
+            v[c].x = in ? fmaf(c4.x, zv[c].x, fmaf(a4.x, g.x, b4.x)) : 0.f;
+            v[c].y = in ? fmaf(c4.y, zv[c].y, fmaf(a4.y, g.y, b4.y)) : 0.f;
+            v[c].z = in ? fmaf(c4.z, zv[c].z, fmaf(a4.z, g.z, b4.z)) : 0.f;
+            v[c].w = in ? fmaf(c4.w, zv[c].w, fmaf(a4.w, g.w, b4.w)) : 0.f;
+          }
+          return;
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int ch = kb * 32 + c * 4;
@@ -573,7 +598,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].w = fmaxf(__fmaf_rn(w2.w, rel[2], __fmaf_rn(w1.w, rel[1], __fmaf_rn(w0.w, rel[0], v[c].w))), 0.f);
           }
         }
-        if (TRAIN && p.in_scale) {
+        if (TRAIN && p.in_scale && p.train_in < 2) {
           // the previous layer's BatchNorm (batch statistics folded to an affine) + ReLU; rows past the end stay zero
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -686,7 +711,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           const int rows_l = p.L[l].rows;
           float *part = s_partial + (tl & 1u) * (4 * 256);
           for (int h = 0; h < nhalf_last; ++h) {
-            TPW(14, &accum_half[h], tl & 1u);
+            TPW(14, &accum_half[(tl & 1u) * 2u + h], (tl >> 1) & 1u);
             tc::tc_fence_after_sync();
             const bool release = nhalf_last == 2 && h == 0;  // half 1 accumulates into the same columns
             if (release && wg * 32 >= rows_l) {              // no chunk for this warpgroup: nothing to drain
@@ -729,21 +754,53 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
                   rvalid = gg < g_here;
                   grow = ((size_t)b * p.M + m0 + gg) * ns + (row - gg * ns);
                 }
-                if (TRAIN && p.stats) {
-                  // column sums over this warp's 32 rows of the raw output and of its square (rows past the end are exact
-                  // zeros: zero operand rows, unit scale, zero shift); butterfly transpose-add: lane j ends with column j
+                if (TRAIN) {
+                  // training passes: raw rows out (forward: z_l; backward: g_{l-1} = da * ReLU mask of the layer below) and
+                  // per-tile column sums over this warp's 32 rows (forward: sum z, sum z^2; backward: sum g, sum g * xhat).
+                  // Rows past the end are exact zeros (zero operand rows, unit scale, zero shift).
                   float sv[32], sq[32];
+                  const size_t rbase = grow * (size_t)cout + c0;
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    const float x = rvalid ? (__uint_as_float(r[i]) + __uint_as_float(r2[i])) : 0.f;
-                    sv[i] = x;
-                    sq[i] = x * x;
+                  for (int c = 0; c < 8; ++c) {
+                    float x[4] = {__uint_as_float(r[c * 4 + 0]) + __uint_as_float(r2[c * 4 + 0]),
+                                  __uint_as_float(r[c * 4 + 1]) + __uint_as_float(r2[c * 4 + 1]),
+                                  __uint_as_float(r[c * 4 + 2]) + __uint_as_float(r2[c * 4 + 2]),
+                                  __uint_as_float(r[c * 4 + 3]) + __uint_as_float(r2[c * 4 + 3])};
+                    float y[4];
+                    const bool in = rvalid && c0 + c * 4 + 3 < cout;
+                    if (p.train_out == 1) {
+                      const float4 zp = in ? __ldg(reinterpret_cast<const float4 *>(p.zprev + rbase + c * 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                      const float zz[4] = {zp.x, zp.y, zp.z, zp.w};
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const int cc = c0 + c * 4 + e;
+                        x[e] = (in && fmaf(zz[e], s_out[cc], s_out[256 + cc]) > 0.f) ? x[e] : 0.f;
+                        y[e] = x[e] * ((zz[e] - s_out[512 + cc]) * s_out[768 + cc]);
+                      }
+                    } else {
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        x[e] = in ? x[e] : 0.f;
+                        y[e] = x[e] * x[e];
+                      }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      sv[c * 4 + e] = x[e];
+                      sq[c * 4 + e] = y[e];
+                    }
+                    if (in) *reinterpret_cast<float4 *>(p.out_pm + rbase + c * 4) = make_float4(x[0], x[1], x[2], x[3]);
                   }
-                  transpose_sum(sv, lane);
-                  transpose_sum(sq, lane);
-                  float *dst = p.stats + ((size_t)(t * 4 + (warp & 3)) * 2) * 256 + c0 + lane;
-                  dst[0] = sv[0];
-                  dst[256] = sq[0];
+                  if (p.stats) {
+                    transpose_sum(sv, lane);
+                    transpose_sum(sq, lane);
+                    float *dst = p.stats + ((size_t)(t * 4 + (warp & 3)) * 2) * 256 + c0 + lane;
+                    dst[0] = sv[0];
+                    dst[256] = sq[0];
+                  }
+                  TP_LAP(18);
+                  continue;
                 }
                 if (rvalid) {
                   float o[32];
@@ -849,6 +906,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
           }
         }
       }
+      if (nl == 1) {  // this tile's accumulators are fully read: the MMA warp may reuse the region (see acc_free there)
+        tc::tc_fence_before_sync();
+        tc::mbar_arrive(&acc_free[tl & 1u]);
+      }
       ++tl;
 #ifdef B200_TC_PROFILE
       ++tp_tiles;
@@ -925,7 +986,7 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float) +
-                       2 * 256 * sizeof(float);
+                       8 * 256 * sizeof(float);
   p.a_stages = (force_astages >= 2 && force_astages <= TP_ASTAGES) ? force_astages : 3;
   p.r1_bytes = p.a_stages * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
@@ -936,9 +997,8 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   B200_CHECK_ARG(p.nslots >= 2, "sa_forward(tc): weight ring does not fit (%d-byte slots)", p.wslot_bytes);
   const size_t smem = rest + (size_t)p.nslots * p.wslot_bytes;
   int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (p.nl == 1 && 2 * grid < p.total_tiles) grid = ceil_div(p.total_tiles, 2);  // at most two tiles per CTA (see publish())
   if (grid <= 0) return 0;
-  if (p.in_scale || p.stats) {
+  if (p.in_scale || p.stats || p.train_in || p.train_out) {
     B200_CHECK_ARG(p.mode == 2 && p.rowout && !p.pre && p.nl == 1, "training pass: one plain-row layer per launch");
     return launch_variant<2, 0, 1, 1>(p, grid, smem, stream);
   }

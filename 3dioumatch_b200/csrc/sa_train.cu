@@ -22,6 +22,7 @@
 #include "../../include/b200_pointnet2.h"
 #include "common.cuh"
 #include "sa_tc.cuh"
+#include "sa_train.cuh"
 
 namespace b200 {
 
@@ -145,16 +146,39 @@ pool_bwd_stats_kernel(long long G, int ns, int CL, const float *__restrict__ z, 
   if (tid == 0) { S1[c] = (float)r1[0]; S2[c] = (float)r2[0]; }
 }
 
+// BatchNorm backward folded to per-channel coefficients:  dz = scale * g + b + c * z  with
+//   b = scale * (m2 * invstd * mean - m1),  c = -scale * m2 * invstd,  m1 = S1 / R,  m2 = S2 / R
+__global__ void __launch_bounds__(256)
+dz_coeff_kernel(int C, float inv_R, const float *__restrict__ mean, const float *__restrict__ invstd,
+                const float *__restrict__ scale, const float *__restrict__ S1, const float *__restrict__ S2,
+                float *__restrict__ coef_b, float *__restrict__ coef_c) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const float m1 = S1[c] * inv_R, m2 = S2[c] * inv_R;
+  coef_b[c] = scale[c] * (m2 * invstd[c] * mean[c] - m1);
+  coef_c[c] = -scale[c] * m2 * invstd[c];
+}
+
+// per-tile column sums of the tensor-core epilogue ([(entry) * 2 + which][256]) -> two vectors, fixed order, fp64
+__global__ void __launch_bounds__(256)
+stats_reduce_kernel(int entries, const float *__restrict__ partial, float *__restrict__ out0, float *__restrict__ out1) {
+  __shared__ double s1[256], s2[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int e = tid; e < entries; e += 256) {
+    a += (double)partial[((size_t)e * 2) * 256 + c];
+    b += (double)partial[((size_t)e * 2 + 1) * 256 + c];
+  }
+  s1[tid] = a; s2[tid] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { s1[tid] += s1[tid + o]; s2[tid] += s2[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) { out0[c] = (float)s1[0]; out1[c] = (float)s2[0]; }
+}
+
 // ---- dz_l built on the fly ----------------------------------------------------------------------------------------------
-struct DzSrc {
-  const float *z;        // (R, C) raw conv output of layer l
-  const float *g;        // (R, C) gradient w.r.t. the BN output with the ReLU mask applied (hidden layers) or NULL (top layer)
-  const float *gout_pm;  // top layer: (G, C) grad_out, point-major
-  const int32_t *arg_pm; // top layer: (G, C) arg-max slot
-  const float *mean, *invstd, *scale, *shift, *S1, *S2;  // (C)
-  int C, ns;
-  float inv_R;
-};
 __device__ __forceinline__ float dz_at(const DzSrc &d, long long r, int c) {
   const float zz = d.z[r * d.C + c];
   float g;
@@ -168,14 +192,6 @@ __device__ __forceinline__ float dz_at(const DzSrc &d, long long r, int c) {
   const float xhat = (zz - d.mean[c]) * d.invstd[c];
   return d.scale[c] * (g - d.S1[c] * d.inv_R - xhat * (d.S2[c] * d.inv_R));
 }
-
-// a_{l-1}: the first layer's input rows as they are, or relu(scale z + shift) of the previous layer
-struct ActSrc {
-  const float *rows;                // (R, ld)
-  const float *scale, *shift;       // NULL: rows are used as they are (layer 1)
-  const float *mean, *invstd;       // for xhat of the previous layer (bwd_da epilogue)
-  int C, ld;
-};
 
 // ---- g_{l-1} = (dz_l W_l) * [a_{l-1} > 0]  (+ column sums of g and g * xhat for the BatchNorm below) ------------------
 // Tile: 64 rows x all cin columns; 256 threads = 16 (row groups of 4) x 16 (column groups of 4 within each 64-column block).
@@ -382,7 +398,7 @@ static bool train_layout(int rows_mode, long long R, int ns, int C0, int L, cons
   for (int l = 0; l < L; ++l) wpart = (size_t)t.cout[l] * t.cin[l] > wpart ? (size_t)t.cout[l] * t.cin[l] : wpart;
   t.ws_bwd = a256(sizeof(float) * (size_t)t.G * t.cout[L - 1]) + (size_t)L * 2 * 256 * sizeof(float) +
              2 * a256(sizeof(float) * (size_t)R * wmax) + a256(sizeof(float) * (size_t)R * t.ld0) +
-             a256(sizeof(float) * 320 * wpart) + a256(sizeof(float) * 2 * 160 * 320);
+             a256(sizeof(float) * 320 * wpart) + a256(sizeof(float) * 2 * 160 * 320) + t.ws_fwd + 4 * 256 * sizeof(float);
   return true;
 }
 
@@ -427,10 +443,13 @@ static int train_forward_rows(const TrainLayout &t, const float *a0, int ns, int
   return 0;
 }
 
+// da0_out: (R, da0_ld) rows receiving the gradient of the first layer's input columns [da0_col0, cin_0) -- packed from
+// column 0 when the tensor-core path ran (*da0_is_full = 0), or the full-width rows of the FFMA fallback (*da0_is_full = 1)
 static int train_backward_rows(const TrainLayout &t, const float *a0, int ns, int B, int M, const b200_bn_layer *layers,
                                const float *grad_out, const uint8_t *saved, float *const *grad_weight,
-                               float *const *grad_gamma, float *const *grad_beta, float *da0_out, uint8_t *ws,
-                               cudaStream_t stream) {
+                               float *const *grad_gamma, float *const *grad_beta, float *da0_out, int da0_col0, int da0_ld,
+                               int *da0_is_full, uint8_t *ws, cudaStream_t stream) {
+  *da0_is_full = 0;
   const int L = t.L, CL = t.cout[L - 1];
   size_t off = 0;
   float *gout_pm = reinterpret_cast<float *>(ws + off); off += a256(sizeof(float) * (size_t)t.G * CL);
@@ -445,7 +464,12 @@ static int train_backward_rows(const TrainLayout &t, const float *a0, int ns, in
   size_t wpart = 0;
   for (int l = 0; l < L; ++l) wpart = (size_t)t.cout[l] * t.cin[l] > wpart ? (size_t)t.cout[l] * t.cin[l] : wpart;
   float *dw_partial = reinterpret_cast<float *>(ws + off); off += a256(sizeof(float) * 320 * wpart);
-  float *st_partial = reinterpret_cast<float *>(ws + off);
+  float *st_partial = reinterpret_cast<float *>(ws + off); off += a256(sizeof(float) * 2 * 160 * 320);
+  float *tc_stats = reinterpret_cast<float *>(ws + off); off += t.ws_fwd;
+  float *coef = reinterpret_cast<float *>(ws + off);  // [b | c | ones | zeros] x 256
+  fill_kernel<<<1, 256, 0, stream>>>(coef + 512, 1.f, 256);
+  B200_LAUNCH_OK("fill_kernel");
+  B200_CUDA_OK(cudaMemsetAsync(coef + 768, 0, 256 * sizeof(float), stream));
   // grad_out (B, CL, M) -> point-major (G, CL)
   {
     const int rc = b200pn2_transpose_cn(B, CL, M, grad_out, gout_pm, 0, (b200_stream_t)stream);
@@ -479,7 +503,30 @@ static int train_backward_rows(const TrainLayout &t, const float *a0, int ns, in
     }
     const int cin = t.cin[l], cout = t.cout[l];
     // dW_l
-    if (grad_weight && grad_weight[l]) {
+    static int use_tc_dw = -1;
+    if (use_tc_dw < 0) {
+      const char *e = getenv("B200_SA_TRAIN_TC");
+      use_tc_dw = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (grad_weight && grad_weight[l] && use_tc_dw && (cout & 3) == 0) {
+      // tensor cores (sa_train_dw.cu): both operands built and transposed on the fly
+      dz_coeff_kernel<<<1, 256, 0, stream>>>(cout, dz.inv_R, dz.mean, dz.invstd, dz.scale, S1, S2, coef, coef + 256);
+      B200_LAUNCH_OK("dz_coeff_kernel");
+      DwParams dp;
+      dp.R = t.R; dp.cin = cin; dp.cout = cout; dp.dz = dz; dp.act = act; dp.coef_b = coef; dp.coef_c = coef + 256;
+      dp.partial = dw_partial;
+      dp.vec_act = ((act.ld & 3) == 0 && (((uintptr_t)act.rows) & 15) == 0) ? 1 : 0;
+      const int otiles = ((cout + 127) / 128) * ((cin + 127) / 128);
+      const long long nkb = (t.R + 31) / 32;
+      int splits = (sms + otiles - 1) / otiles;
+      if (splits > 320) splits = 320;
+      if (splits > nkb) splits = (int)nkb;
+      const int rc = dw_tc_launch(dp, splits, stream);
+      if (rc) return rc;
+      reduce_partials_kernel<<<(cout * cin + 255) / 256, 256, 0, stream>>>(splits, cout * cin, (size_t)cout * cin, dw_partial,
+                                                                          grad_weight[l]);
+      B200_LAUNCH_OK("reduce_partials_kernel");
+    } else if (grad_weight && grad_weight[l]) {
       const int otiles = ((cout + 63) / 64) * ((cin + 63) / 64);
       long long chunks = (t.R + 31) / 32;
       int splits = (2 * sms + otiles - 1) / otiles;
@@ -491,29 +538,64 @@ static int train_backward_rows(const TrainLayout &t, const float *a0, int ns, in
                                                                           grad_weight[l]);
       B200_LAUNCH_OK("reduce_partials_kernel");
     }
-    // g_{l-1} (or da_0)
+    // g_{l-1} (or da_0: only the columns of the caller's features, da0_col0 onwards)
     const bool need_da = l > 0 || da0_out != nullptr;
     if (need_da) {
-      const int cin_s = ((cin + 63) / 64) * 64;
-      const size_t smem = sizeof(float) * ((size_t)cout * cin_s + (size_t)DA_TR * (cout + 1));
-      const size_t smem_red = sizeof(float) * 16 * (size_t)cin_s;
-      const size_t smem_all = smem > smem_red ? smem : smem_red;
-      B200_CHECK_ARG(smem_all <= 227 * 1024, "sa_train_backward: layer %d (%d -> %d) needs %zu B of shared memory", l, cin, cout, smem_all);
-      static DynSmemOptIn optin;
-      B200_CUDA_OK(optin.ensure(bwd_da_kernel, smem_all));
-      const long long tiles = (t.R + DA_TR - 1) / DA_TR;
-      int grid = tiles < sms ? (int)tiles : sms;
-      if (grid > 160) grid = 160;
+      const int col0 = l == 0 ? da0_col0 : 0;
+      const int n_out = cin - col0;
       float *g_next = l == 0 ? da0 : gbuf[l & 1];
-      bwd_da_kernel<<<grid, 256, smem_all, stream>>>(t.R, cin, cout, cin_s, dz, layers[l].weight, act, g_next,
-                                                    l == 0 ? t.ld0 : cin, l == 0 ? nullptr : st_partial);
-      B200_LAUNCH_OK("bwd_da_kernel");
-      if (l > 0) {
-        float *n1 = S + (size_t)(l - 1) * 512, *n2 = n1 + 256;
-        reduce_partials_kernel<<<(cin + 255) / 256, 256, 0, stream>>>(grid, cin, (size_t)2 * cin_s, st_partial, n1);
-        B200_LAUNCH_OK("reduce_partials_kernel");
-        reduce_partials_kernel<<<(cin + 255) / 256, 256, 0, stream>>>(grid, cin, (size_t)2 * cin_s, st_partial + cin_s, n2);
-        B200_LAUNCH_OK("reduce_partials_kernel");
+      float *n1 = l > 0 ? S + (size_t)(l - 1) * 512 : nullptr, *n2 = l > 0 ? n1 + 256 : nullptr;
+      static int use_tc = -1;
+      if (use_tc < 0) {
+        const char *e = getenv("B200_SA_TRAIN_TC");
+        use_tc = (e && atoi(e) == 0) ? 0 : 1;
+      }
+      if (use_tc && (cout & 3) == 0 && (n_out & 3) == 0 && n_out <= 256) {
+        // tensor cores: the forward's row-GEMM kernel on W_l^T, dz built in its producers, ReLU mask + statistics of
+        // the layer below in its epilogue
+        dz_coeff_kernel<<<1, 256, 0, stream>>>(cout, dz.inv_R, dz.mean, dz.invstd, dz.scale, S1, S2, coef, coef + 256);
+        B200_LAUNCH_OK("dz_coeff_kernel");
+        b200_mlp_layer lay;
+        lay.cin = cout; lay.cout = n_out; lay.weight = layers[l].weight + col0; lay.scale = coef + 512; lay.shift = coef + 768;
+        TcCall c;
+        c.mode = 2; c.B = 1; c.N = (int)t.R; c.M = (int)t.R; c.C = cout; c.ld = cout; c.ns = 32; c.use_xyz = 0;
+        c.feat_pm = dz.z; c.rowout = 1; c.final_relu = 0; c.rows_total = (int)t.R; c.rows_per_scene = (int)t.R;
+        c.out_pm = g_next; c.num_layers = 1; c.layers = &lay; c.w_transposed = 1; c.w_ld = cin;
+        c.train_in = dz.g ? 2 : 3; c.in_scale = dz.scale; c.in_shift = dz.shift; c.dz_b = coef; c.dz_c = coef + 256;
+        c.g_rows = dz.g; c.gout_pm = dz.gout_pm; c.arg_pm = dz.arg_pm; c.pool_ns = ns;
+        if (l > 0) {
+          c.train_out = 1; c.zprev = act.rows; c.out_scale = act.scale; c.out_shift = act.shift; c.out_mean = act.mean;
+          c.out_invstd = act.invstd; c.stats = tc_stats;
+        }
+        const int rc = sa_tc_run(c, stream);
+        if (rc) return rc;
+        if (l > 0) {
+          stats_reduce_kernel<<<cin, 256, 0, stream>>>((int)(t.tiles * 4), tc_stats, n1, n2);
+          B200_LAUNCH_OK("stats_reduce_kernel");
+        }
+      } else {
+        // fp32 FFMA fallback (widths that are no multiple of 4): full-width rows, then the caller's columns are read with col0
+        B200_CHECK_ARG(l > 0 || col0 == 0 || da0_ld == t.ld0, "sa_train_backward: internal layout error");
+        const int cin_s = ((cin + 63) / 64) * 64;
+        const size_t smem = sizeof(float) * ((size_t)cout * cin_s + (size_t)DA_TR * (cout + 1));
+        const size_t smem_red = sizeof(float) * 16 * (size_t)cin_s;
+        const size_t smem_all = smem > smem_red ? smem : smem_red;
+        B200_CHECK_ARG(smem_all <= 227 * 1024, "sa_train_backward: layer %d (%d -> %d) needs %zu B of shared memory", l, cin, cout, smem_all);
+        static DynSmemOptIn optin;
+        B200_CUDA_OK(optin.ensure(bwd_da_kernel, smem_all));
+        const long long tiles = (t.R + DA_TR - 1) / DA_TR;
+        int grid = tiles < sms ? (int)tiles : sms;
+        if (grid > 160) grid = 160;
+        bwd_da_kernel<<<grid, 256, smem_all, stream>>>(t.R, cin, cout, cin_s, dz, layers[l].weight, act, g_next,
+                                                      l == 0 ? t.ld0 : cin, l == 0 ? nullptr : st_partial);
+        B200_LAUNCH_OK("bwd_da_kernel");
+        if (l > 0) {
+          reduce_partials_kernel<<<(cin + 255) / 256, 256, 0, stream>>>(grid, cin, (size_t)2 * cin_s, st_partial, n1);
+          B200_LAUNCH_OK("reduce_partials_kernel");
+          reduce_partials_kernel<<<(cin + 255) / 256, 256, 0, stream>>>(grid, cin, (size_t)2 * cin_s, st_partial + cin_s, n2);
+          B200_LAUNCH_OK("reduce_partials_kernel");
+        }
+        if (l == 0) *da0_is_full = 1;
       }
       g_cur = g_next;
     }
@@ -588,20 +670,22 @@ extern "C" int b200pn2_sa_train_backward(int B, int N, int M, int C, int nsample
   const float *a0 = rows_mode ? x_rows : reinterpret_cast<const float *>((const uint8_t *)saved + t.off_a0);
   float *da0 = nullptr;
   ScratchGuard da_guard;
+  const int col0 = (!rows_mode && use_xyz) ? 3 : 0;
   if (rows_mode && grad_rows) {
     da0 = grad_rows;  // (R, C) with ld0 == C in rows mode
   } else if (!rows_mode && grad_features && C > 0) {
     B200_CUDA_OK(da_guard.alloc(sizeof(float) * (size_t)t.R * t.ld0, stream));
     da0 = (float *)da_guard.ptr;
   }
+  int full = 0;
   const int rc = train_backward_rows(t, a0, nsample, B, M, layers, grad_out, (const uint8_t *)saved, grad_weight, grad_gamma,
-                                     grad_beta, da0, (uint8_t *)workspace, stream);
+                                     grad_beta, da0, col0, t.ld0, &full, (uint8_t *)workspace, stream);
   if (rc) return rc;
   if (!rows_mode && grad_features && C > 0) {
     B200_CHECK_ARG(idx, "sa_train_backward: idx needed for the feature gradient");
     B200_CUDA_OK(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)B * C * N, stream));
-    rows_scatter_kernel<<<(unsigned)((t.R + 7) / 8), 256, 0, stream>>>(t.R, N, M, nsample, C, t.ld0, use_xyz ? 3 : 0, da0, idx,
-                                                                       grad_features);
+    rows_scatter_kernel<<<(unsigned)((t.R + 7) / 8), 256, 0, stream>>>(t.R, N, M, nsample, C, full ? t.ld0 : C, full ? col0 : 0,
+                                                                       da0, idx, grad_features);
     B200_LAUNCH_OK("rows_scatter_kernel");
   }
   return 0;

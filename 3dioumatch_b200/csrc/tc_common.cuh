@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace b200 {
 namespace tc {
@@ -148,4 +149,43 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 }
 
 }  // namespace tc
+
+// mbarrier wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_addr(bar);
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin == 256) t0 = clock64();
+    if (spin > 256 && (spin & 255u) == 0u && clock64() - t0 > 6000000000LL) {
+      printf("[b200] tensor-core kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+
+// one leader lane of a converged warp (the same lane every time: tcgen05.commit tracks the issuing thread)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 }  // namespace b200

@@ -199,6 +199,7 @@ def test_d_fast_callers_mirrors_match_the_reference(world):
     sd_f, sd_r = net_f.state_dict(), world["net_r"].state_dict()
     assert sd_f.keys() == sd_r.keys() and all(torch.equal(sd_f[k], sd_r[k]) for k in sd_f)
     from torch.profiler import ProfilerActivity, profile
+    fast.pt.freeze_inference(net_f)
     with torch.no_grad():
         ra.forward_with_iou_labels(fast, net_f, cfg_f, world["pc"], world["labels"])
         torch.cuda.synchronize()

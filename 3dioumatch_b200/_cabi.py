@@ -27,6 +27,7 @@ PROTOTYPES = {
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200pn2_fps_set_policy": (c_int, [c_int]),
+    "b200pn2_fps_force_shape": (c_int, [c_int, c_int, c_int]),
     "b200pn2_furthest_point_sampling": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -132,3 +133,9 @@ def set_fps_policy(policy):
     names = ("latency", "throughput")
     prev = lib().b200pn2_fps_set_policy(names.index(policy))
     return names[prev]
+
+
+def force_fps_shape(kernel=-1, cluster=0, threads=0):
+    """Tuning / test hook: kernel 0 fps_owner_kernel wherever it applies, 2 fps_cluster_kernel (round 1), -1 default;
+    cluster / threads 0 = cost model (include/b200_pointnet2.h: b200pn2_fps_force_shape)."""
+    lib().b200pn2_fps_force_shape(int(kernel), int(cluster), int(threads))

@@ -19,6 +19,7 @@
 //     (bitrev_L(k mod bs) << 22) | (k >> L).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <string.h>
 
 #include "../../include/b200_pointnet2.h"
 #include "common.cuh"
@@ -313,6 +314,237 @@ fps_cluster_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, in
   if (CS > 1) cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
+// ---- fps_owner_kernel: value-only reduction, the owning lane identifies the winner -----------------------------------
+// Second-generation register-resident kernel for the cluster shapes with many warps per SM.  fps_cluster_kernel above
+// carries (value, tie key, index) through every level of the arg-max, which costs every thread a 3-instruction-per-
+// point slot tournament and every warp the key arithmetic: ~160 update + ~190 reduction instructions per
+// warp-iteration, issue- and ALU-pipe-bound at 16 warps per SM (profiles/r2_fps_cluster_kernel_warpstate.txt).  Here
+// only the VALUE is reduced (20 FMNMX + 10 three-input FMNMX3 per thread, one redux per warp, one shared-memory hop
+// per CTA); the point that owns the CTA maximum is looked up afterwards by the lanes whose running maximum equals it
+// -- normally one lane of one warp; every other warp goes straight to the mbarrier wait.  Exact ties (duplicated
+// points; the reference's bit-reversed tree order, see the file header) are resolved among the tied lanes / warps
+// only: redux.min over their tie keys, and a named barrier that just the tied warps join.  The owning warp pushes the
+// CTA's 32-byte record {value, key | x, y, z, index} to every peer with st.async (cluster) or stores it locally and
+// arrives on the mbarrier (single CTA).  Measured (B=8, N=40000 -> 2048, 4 CTAs x 512 threads per scene): 2.27 -> 1.69 ms.
+// Also measured and dropped: one flat exchange of per-WARP records (no CTA-level step; every thread reduces the 64
+// records of the scene): 2.26 ms -- 128 st.async per CTA-iteration cost more than the barrier they replace.
+// Same results as fps_cluster_kernel bit for bit (tests/test_gpu_pointops.py runs every shape of both).
+struct __align__(16) FpsRecord2 {
+  int v;         // float bits of the CTA's best min-distance (negative: the CTA has no candidate)
+  unsigned key;  // tie key of that point
+  int pad0, pad1;
+  float x, y, z;
+  int k;         // its index
+};
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// maximum of N registers as a tree of three-input FMNMX3 (N = 20: 7 + 3 + 1 instructions)
+template <int N>
+__device__ __forceinline__ float max_tree(const float (&t)[N]) {
+  if constexpr (N == 1) {
+    return t[0];
+  } else {
+    constexpr int O = (N + 2) / 3;
+    float o[O];
+#pragma unroll
+    for (int i = 0; i < O; ++i) {
+      if (3 * i + 2 < N)
+        o[i] = fmax3(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+      else if (3 * i + 1 < N)
+        o[i] = fmaxf(t[3 * i], t[3 * i + 1]);
+      else
+        o[i] = t[3 * i];
+    }
+    return max_tree<O>(o);
+  }
+}
+
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS, 1)
+fps_owner_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
+  constexpr int NWARP = THREADS / 32;
+  extern __shared__ float4 s_tab[];  // [PPT][THREADS] coordinates of this CTA's points: the owner's one LDS.128
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned CS = cluster.num_blocks();  // power of two
+  const unsigned rank = cluster.block_rank();
+  const int b = blockIdx.y;
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = (int)CS * THREADS;  // threads per scene, a power of two and a multiple of bs (the launcher checks)
+  const int g = (int)rank * THREADS + tid;
+  const float *pts = xyz + (size_t)b * N * 3;
+  int32_t *out = idx + (size_t)b * m;
+
+  __shared__ int s_v[2][NWARP];
+  __shared__ unsigned s_key2[2][NWARP];
+  __shared__ FpsRecord2 s_slot[2][16];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float px[PPT], py[PPT], pz[PPT], pt[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int k = g + p * T;
+    if (k < N) {
+      px[p] = pts[(size_t)k * 3 + 0];
+      py[p] = pts[(size_t)k * 3 + 1];
+      pz[p] = pts[(size_t)k * 3 + 2];
+      const float mag = sq3(px[p], py[p], pz[p]);     // sampling_gpu.cu:105
+      pt[p] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;  // :106 skipped points never compete; temp = 1e10 otherwise
+    } else {
+      px[p] = py[p] = pz[p] = 0.f;
+      pt[p] = -1.0f;
+    }
+    s_tab[p * THREADS + tid] = make_float4(px[p], py[p], pz[p], 0.f);
+  }
+  if (CS > 1) cluster.sync(); else __syncthreads();  // barriers exist before any peer signals them; table visible
+
+  const unsigned bsmask = (1u << L) - 1u;
+  auto tie_key = [&](int k) -> unsigned {
+    const unsigned rev = L > 0 ? (__brev((unsigned)k & bsmask) >> (32 - L)) : 0u;
+    return (rev << 22) | ((unsigned)k >> L);
+  };
+  // remote addresses of this CTA's record slot and of the mbarrier in peer `lane`, for both parities (loop invariant)
+  unsigned r_dst0 = 0u, r_dst1 = 0u, r_bar0 = 0u, r_bar1 = 0u;
+  if (CS > 1 && lane < (int)CS) {
+    r_dst0 = map_to_rank(smem_u32(&s_slot[0][rank]), (unsigned)lane);
+    r_dst1 = map_to_rank(smem_u32(&s_slot[1][rank]), (unsigned)lane);
+    r_bar0 = map_to_rank(smem_u32(&s_bar[0]), (unsigned)lane);
+    r_bar1 = map_to_rank(smem_u32(&s_bar[1]), (unsigned)lane);
+  }
+  const float x0 = pts[0], y0 = pts[1], z0 = pts[2];
+  float cx = x0, cy = y0, cz = z0;  // idx[0] = 0 (:89-92)
+  if (rank == 0 && tid == 0) out[0] = 0;
+
+  for (int j = 1; j < m; ++j) {
+    const int par = j & 1;
+    const unsigned r_dst = par ? r_dst1 : r_dst0, r_bar = par ? r_bar1 : r_bar0;
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[par], CS * (unsigned)sizeof(FpsRecord2));
+    // ---- distance update (packed pairs, the reference's rounding sequence) + value-only maximum ----------------------
+    const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
+#pragma unroll
+    for (int p = 0; p + 1 < PPT; p += 2) {
+      float d0, d1;
+      unpack2(sqdist3_x2(pack2(px[p], px[p + 1]), pack2(py[p], py[p + 1]), pack2(pz[p], pz[p + 1]), cx2, cy2, cz2), d0, d1);
+      pt[p] = fminf(d0, pt[p]);  // :108-111
+      pt[p + 1] = fminf(d1, pt[p + 1]);
+    }
+    if (PPT & 1) {
+      constexpr int p = PPT - 1;
+      pt[p] = fminf(sqdist3(px[p], py[p], pz[p], cx, cy, cz), pt[p]);
+    }
+    const float tmax = max_tree<PPT>(pt);  // >= +0, or -1.0f when this thread has no candidate
+    const int v = __float_as_int(tmax);    // signed-int order == float order on that range
+    const int Vw = __reduce_max_sync(0xffffffffu, v);
+    int Vc = Vw, cv = Vw;
+    if (NWARP > 1) {
+      if (lane == 0) s_v[par][warp] = Vw;
+      __syncthreads();
+      cv = lane < NWARP ? s_v[par][lane] : (int)0x80000000;
+      Vc = __reduce_max_sync(0xffffffffu, cv);
+    }
+    // ---- the CTA's record: identified and sent by the warp that owns the maximum --------------------------------------
+    if (Vc < 0) {  // no candidate in this CTA: the reference's (best = -1, besti = 0) state
+      if (warp == 0) {
+        if (CS > 1) {
+          if (lane < (int)CS) {
+            st_async_v4(r_dst, r_bar, (unsigned)Vc, 0xffffffffu, 0u, 0u);
+            st_async_v4(r_dst + 16, r_bar, 0u, 0u, 0u, 0u);
+          }
+        } else if (lane == 0) {
+          s_slot[par][0].v = Vc;
+          mbar_arrive(&s_bar[par]);
+        }
+      }
+    } else if (Vw == Vc) {
+      const bool mine = (v == Vc);
+      unsigned key = 0xffffffffu;
+      int bk = 0;
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mine) {  // ascending slot == ascending key inside a thread (T is a multiple of bs): the FIRST matching slot
+        int slot = 0;
+#pragma unroll
+        for (int p = PPT - 1; p >= 0; --p) slot = (pt[p] == tmax) ? p : slot;
+        bk = g + slot * T;
+        key = tie_key(bk);
+        c = s_tab[slot * THREADS + tid];
+      }
+      const unsigned tied = __ballot_sync(0xffffffffu, mine);
+      int src = __ffs(tied) - 1;
+      unsigned wkey;
+      if (tied & (tied - 1u)) {  // rare: several lanes hold the maximum -> smallest key
+        wkey = __reduce_min_sync(0xffffffffu, key);
+        src = __ffs(__ballot_sync(0xffffffffu, key == wkey)) - 1;
+      } else {
+        wkey = __shfl_sync(0xffffffffu, key, src);
+      }
+      bool win = true;
+      if (NWARP > 1) {
+        const unsigned cand = __ballot_sync(0xffffffffu, cv == Vc);  // warps tied at the CTA maximum
+        if (cand & (cand - 1u)) {  // rare: only the tied warps meet, on their own named barrier
+          if (lane == 0) s_key2[par][warp] = wkey;
+          asm volatile("bar.sync 1, %0;" ::"r"(32 * __popc(cand)) : "memory");
+          const unsigned ck = ((cand >> lane) & 1u) ? s_key2[par][lane] : 0xffffffffu;
+          win = (wkey == __reduce_min_sync(0xffffffffu, ck));  // keys are unique per point
+        }
+      }
+      if (win) {
+        bk = __shfl_sync(0xffffffffu, bk, src);
+        c.x = __shfl_sync(0xffffffffu, c.x, src);
+        c.y = __shfl_sync(0xffffffffu, c.y, src);
+        c.z = __shfl_sync(0xffffffffu, c.z, src);
+        if (CS > 1) {
+          if (lane < (int)CS) {
+            st_async_v4(r_dst, r_bar, (unsigned)Vc, wkey, 0u, 0u);
+            st_async_v4(r_dst + 16, r_bar, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z),
+                        (unsigned)bk);
+          }
+        } else if (lane == 0) {
+          s_slot[par][0].v = Vc;
+          *reinterpret_cast<float4 *>(&s_slot[par][0].x) = make_float4(c.x, c.y, c.z, __int_as_float(bk));
+          mbar_arrive(&s_bar[par]);
+        }
+      }
+    }
+    mbar_wait(&s_bar[par], (unsigned)(((j - 1) >> 1) & 1));
+    // ---- arg-max over the CS records (value; tie key only when values tie) -------------------------------------------
+    int bvv;
+    float4 w;
+    if (CS > 1) {
+      uint2 t = make_uint2(0x80000000u, 0xffffffffu);
+      if (lane < (int)CS) t = *reinterpret_cast<const uint2 *>(&s_slot[par][lane]);
+      bvv = __reduce_max_sync(0xffffffffu, (int)t.x);
+      unsigned cand = __ballot_sync(0xffffffffu, (int)t.x == bvv);
+      if (cand & (cand - 1u)) {
+        const unsigned mk = __reduce_min_sync(0xffffffffu, (int)t.x == bvv ? t.y : 0xffffffffu);
+        cand = __ballot_sync(0xffffffffu, (int)t.x == bvv && t.y == mk);
+      }
+      w = *reinterpret_cast<const float4 *>(&s_slot[par][__ffs(cand) - 1].x);
+    } else {
+      bvv = s_slot[par][0].v;
+      w = *reinterpret_cast<const float4 *>(&s_slot[par][0].x);
+    }
+    int wk = __float_as_int(w.w);
+    if (bvv < 0) {  // every candidate skipped: the reference's besti stays 0 everywhere
+      wk = 0; w.x = x0; w.y = y0; w.z = z0;
+    }
+    cx = w.x; cy = w.y; cz = w.z;
+    if (rank == 0 && tid == 0) out[j] = wk;  // :175-176
+  }
+  if (CS > 1) cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
+}
+
 // ---- large-N fallback: min-distances in global scratch, one 1024-thread CTA per scene -----------
 __global__ void __launch_bounds__(1024, 1)
 fps_global_kernel(int N, int m, int L, const float *__restrict__ xyz, float *__restrict__ temp,
@@ -385,15 +617,29 @@ static fps_fn pick_ppt(int ppt, int *ppt_out) {
   return nullptr;
 }
 
-// two scenes per 512-thread CTA (256 threads each; fps_cluster_kernel<512, P, 1, 2>)
-static fps_fn pick_grouped(int ppt, int *ppt_out) {
-#define B200_FPS_CASE(P)                      \
-  if (ppt <= P) {                             \
-    *ppt_out = P;                             \
-    return fps_cluster_kernel<512, P, 1, 2>;  \
+template <int THREADS>
+static fps_fn pick_owner_ppt(int ppt, int *ppt_out) {
+  constexpr int MAXP = THREADS >= 512 ? 20 : 32;
+#define B200_FPS_CASE(P)                     \
+  if (P <= MAXP && ppt <= P) {               \
+    *ppt_out = P;                            \
+    return fps_owner_kernel<THREADS, (P <= MAXP ? P : 1)>; \
   }
-  B200_FPS_CASE(8) B200_FPS_CASE(12) B200_FPS_CASE(16) B200_FPS_CASE(20)
+  B200_FPS_CASE(1) B200_FPS_CASE(2) B200_FPS_CASE(4) B200_FPS_CASE(6) B200_FPS_CASE(8) B200_FPS_CASE(10)
+  B200_FPS_CASE(12) B200_FPS_CASE(16) B200_FPS_CASE(20) B200_FPS_CASE(24) B200_FPS_CASE(32)
 #undef B200_FPS_CASE
+  *ppt_out = 0;
+  return nullptr;
+}
+
+static fps_fn pick_owner(int threads, int ppt, int *ppt_out) {
+  switch (threads) {
+    case 32: return pick_owner_ppt<32>(ppt, ppt_out);
+    case 64: return pick_owner_ppt<64>(ppt, ppt_out);
+    case 128: return pick_owner_ppt<128>(ppt, ppt_out);
+    case 256: return pick_owner_ppt<256>(ppt, ppt_out);
+    case 512: return pick_owner_ppt<512>(ppt, ppt_out);
+  }
   *ppt_out = 0;
   return nullptr;
 }
@@ -461,6 +707,17 @@ extern "C" int b200pn2_fps_set_policy(int policy) {
   return prev;
 }
 
+// tuning / test hook: force the kernel generation (0 fps_owner_kernel wherever it applies, 2 fps_cluster_kernel;
+// -1 = B200_FPS_KERNEL / default: owner for cluster shapes, fps_cluster_kernel for single-CTA shapes) and the launch
+// shape (0 = cost model).  Results are identical for every choice.
+static std::atomic<int> g_fps_force[3] = {{-1}, {0}, {0}};
+extern "C" int b200pn2_fps_force_shape(int kernel, int cluster, int threads) {
+  g_fps_force[0].store(kernel, std::memory_order_relaxed);
+  g_fps_force[1].store(cluster, std::memory_order_relaxed);
+  g_fps_force[2].store(threads, std::memory_order_relaxed);
+  return 0;
+}
+
 extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx, float *scratch,
                                                b200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -478,26 +735,31 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   }
 #endif
   // Launch shape: (cluster size, threads per CTA, points per thread).  Candidates must hold the cloud in registers;
-  // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py): the update is issue-bound
-  // (~9 cycles per point per warp sharing a scheduler), each level of the arg-max tree adds a fixed latency.
-  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0, env_pack = 0, env_groups = -1;
+  // the cheapest per-iteration cost wins (model calibrated on B200, scripts/op_sweep.py fps_shapes): the update is
+  // issue-bound (cycles per point per warp sharing a scheduler), each level of the arg-max adds a fixed latency.
+  // B200_FPS_KERNEL = auto (default: fps_owner_kernel for cluster shapes) | owner | v1 (fps_cluster_kernel everywhere).
+  static int env_cs = -1, env_threads = -1, env_min_n = 0, debug = 0, env_kernel = -1;
   if (env_cs < 0) {
-    const char *eg = getenv("B200_FPS_GROUPS");  // 1: allow two scenes per CTA (fps_cluster_kernel<512, P, 1, 2>)
-    env_groups = eg ? atoi(eg) : 0;
-    const char *ep = getenv("B200_FPS_PACK");  // 1: two CTAs per SM for the large-cloud shapes (pick_kernel2)
-    env_pack = ep ? atoi(ep) : 0;
-    const char *e = getenv("B200_FPS_CLUSTER");
-    env_cs = e ? atoi(e) : 0;
-    e = getenv("B200_FPS_THREADS");
+    const char *ek = getenv("B200_FPS_KERNEL");
+    env_kernel = !ek ? -1 : (!strcmp(ek, "v1") ? 2 : (!strcmp(ek, "owner") ? 0 : -1));
+    const char *e = getenv("B200_FPS_THREADS");
     env_threads = e ? atoi(e) : 0;
-    e = getenv("B200_FPS_FORCE_MIN_N");  // the two overrides above apply to clouds of at least this many points
+    e = getenv("B200_FPS_FORCE_MIN_N");  // the two shape overrides apply to clouds of at least this many points
     env_min_n = e ? atoi(e) : 0;
     debug = getenv("B200_FPS_DEBUG") != nullptr;
+    e = getenv("B200_FPS_CLUSTER");
+    env_cs = e ? atoi(e) : 0;
   }
-  const int force_cs = N >= env_min_n ? env_cs : 0, force_threads = N >= env_min_n ? env_threads : 0;
+  const int f_kernel = g_fps_force[0].load(std::memory_order_relaxed), f_cs = g_fps_force[1].load(std::memory_order_relaxed),
+            f_th = g_fps_force[2].load(std::memory_order_relaxed);
+  const int kernel_sel = f_kernel >= 0 ? f_kernel : env_kernel;
+  const int force_cs = f_cs > 0 ? f_cs : (N >= env_min_n ? env_cs : 0);
+  const int force_threads = f_th > 0 ? f_th : (N >= env_min_n ? env_threads : 0);
   const int sms = num_sms();
   const bool throughput = fps_policy() == 1;
-  int best_cs = 0, best_ppt = 0, threads = 0, best_groups = 1;
+  // kernel_sel: -1 auto, 0 owner wherever it applies, 2 v1
+  int best_cs = 0, best_ppt = 0, threads = 0;
+  bool best_own = false;
   fps_fn best_fn = nullptr;
   double best_cost = 1e300;
   const int cs_list[5] = {1, 2, 4, 8, 16};
@@ -510,13 +772,19 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       if (force_threads > 0 && th != force_threads) continue;
       if (cs > 1 && N < cs * th) continue;  // do not spread fewer than one point per thread
       // keep (threads per scene) a multiple of the reference block size whenever some candidate allows it: all points
-      // of a thread then share k mod bs and the per-thread tie pass is skipped (measured ~2x cheaper update)
+      // of a thread then share k mod bs and no per-thread tie pass is needed
       if (((cs * th) % bs) != 0 && force_threads <= 0 && force_cs <= 0) continue;
       const int need = ceil_div(N, cs * th);
       int ppt = 0;
-      fps_fn fn = pick_kernel(th, need, &ppt);
+      const bool ties = ((cs * th) % bs) != 0;
+      // fps_owner_kernel: threads per scene a multiple of bs (exact ties inside a thread need the keyed tournament of
+      // fps_cluster_kernel); by default only for the issue-bound shape it was built for -- clusters of 512-thread CTAs
+      // (measured, B=8 N=40000: 4x512 2.27 -> 1.69 ms, 8x256 1.35 -> 1.32 ms; single-CTA and 128-thread shapes are
+      // latency chains and stay faster on fps_cluster_kernel, which has no slot search on the critical path)
+      const bool own = kernel_sel != 2 && !ties && (kernel_sel == 0 || (cs > 1 && th >= 256));
+      fps_fn fn = !own ? pick_kernel(th, need, &ppt) : pick_owner(th, need, &ppt);
       if (!fn) continue;
-      const size_t smem = sizeof(float) * 3 * (size_t)ppt * th;
+      const size_t smem = (own ? sizeof(float4) : 3 * sizeof(float)) * (size_t)ppt * th;
       if (smem > 200 * 1024) continue;
       if (smem > 40 * 1024 &&
           cudaFuncSetAttribute((void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -532,46 +800,23 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
       if (conc <= 0) continue;
       const int waves = ceil_div(B, conc);
       const int warps_per_sched = th >= 128 ? th / 128 : 1;
-      const bool ties = ((cs * th) % bs) != 0;
-      const double iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
-                          (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 260.0 : 0.0);  // >8: non-portable size; also keeps half the SMs free for the feature kernels
+      double iter;
+      if (own)  // value-only update; the owner's slot search, the barrier and the exchange are the fixed part
+        iter = 6.5 * ppt * warps_per_sched + 60.0 + (th > 32 ? 130.0 + 6.0 * (th / 32) : 0.0) + (cs > 1 ? 780.0 : 330.0) +
+               (cs > 8 ? 260.0 : 0.0);
+      else
+        iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
+               (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 260.0 : 0.0);  // >8: non-portable size; also keeps half the SMs free
       // latency policy: serial chain length; throughput policy: SM-cycles per scene (cs CTAs hold an SM each)
       const double cost = throughput ? waves * iter * cs : waves * iter;
       if (cost < best_cost) {
-        best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th; best_groups = 1;
-      }
-      // two scenes per CTA (256 threads each): the pair costs one CTA-iteration of ~1.25x the single-scene length
-      // Measured (B=8, N=40000): 2.50 ms for the paired shape against 2.27 ms for one scene per 512-thread CTA on the
-      // same 32 SMs -- at 16 warps the SM is issue-bound (~300 instructions per warp-iteration at IPC 0.6), not
-      // latency-bound, so a second scene has no idle slots to fill.  Bit-exact, kept opt-in (B200_FPS_GROUPS=1).
-      const bool groups_ok = env_groups == 1;
-      if (groups_ok && th == 256 && B >= 2 && N >= 8192 && !ties) {
-        int gppt = 0;
-        fps_fn gfn = pick_grouped(need, &gppt);
-        const size_t gsmem = 2 * sizeof(float) * 3 * (size_t)gppt * 256;
-        if (gfn && gsmem <= 200 * 1024 &&
-            cudaFuncSetAttribute((void *)gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem) == cudaSuccess &&
-            (cs <= 8 ||
-             cudaFuncSetAttribute((void *)gfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
-          const int gconc = cs == 1 ? sms : max_clusters(gfn, 512, cs, gsmem);
-          if (gconc > 0) {
-            const int gwaves = ceil_div(ceil_div(B, 2), gconc);
-            const double giter = 1.25 * (10.5 * gppt * 2 + 120.0 + 120.0 + 6.0 * 8 + (cs > 1 ? 620.0 : 0.0) +
-                                         (cs > 8 ? 260.0 : 0.0));
-            const double gcost = throughput ? gwaves * giter * cs / 2.0 : gwaves * giter;
-            if (gcost < best_cost) {
-              best_cost = gcost; best_cs = cs; best_ppt = gppt; best_fn = gfn; threads = 512; best_groups = 2;
-            }
-          }
-        } else {
-          cudaGetLastError();
-        }
+        best_cost = cost; best_cs = cs; best_ppt = ppt; best_fn = fn; threads = th; best_own = own;
       }
     }
   }
   if (debug)
-    fprintf(stderr, "[b200 fps] B=%d N=%d m=%d -> cluster=%d threads=%d ppt=%d scenes/CTA=%d (model cost %.0f)\n", B, N, m,
-            best_cs, threads, best_ppt, best_groups, best_cost);
+    fprintf(stderr, "[b200 fps] B=%d N=%d m=%d -> %s cluster=%d threads=%d ppt=%d (model cost %.0f)\n", B, N, m,
+            best_own ? "owner" : "v1", best_cs, threads, best_ppt, best_cost);
 
   if (!best_fn) {
     // cloud too large for the register-resident kernel
@@ -582,9 +827,9 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   }
 
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(best_cs, ceil_div(B, best_groups), 1);
+  cfg.gridDim = dim3(best_cs, B, 1);
   cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = sizeof(float) * 3 * (size_t)best_ppt * threads;  // both groups' coordinate tables
+  cfg.dynamicSmemBytes = (best_own ? sizeof(float4) : 3 * sizeof(float)) * (size_t)best_ppt * threads;  // coordinate table
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -594,6 +839,6 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   cfg.attrs = at;
   cfg.numAttrs = 1;
   B200_CUDA_OK(cudaLaunchKernelEx(&cfg, best_fn, B, N, m, L, xyz, idx));
-  B200_LAUNCH_OK("fps_cluster_kernel");
+  B200_LAUNCH_OK(best_own ? "fps_owner_kernel" : "fps_cluster_kernel");
   return 0;
 }

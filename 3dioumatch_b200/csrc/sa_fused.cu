@@ -482,8 +482,13 @@ extern "C" int b200pn2_sa_forward_planned(int B, int N, int M, int C, float radi
   // query has to produce
   const float *fpm = features_pm;
   if (C == 1 && !fpm) fpm = features;  // (B,1,N) and (B,N,1) are the same memory
+  // fused ball query (north-star shape of the op): for the small levels the tensor-core kernel's producers stage the
+  // scene in shared memory and run the radius search themselves -- no query launch, no idx round trip
+  const bool tc_maybe = sa_tc_supported(C, nsample, use_xyz, num_layers, layers, fpm ? fpm : (C > 1 ? features : nullptr));
+  const bool fuse_query = !idx_in && tc_maybe && !sa_tcp_units_wanted(0, 0, nsample, B, M) &&
+                          sa_tcp_query_fusable(B, N, M, nsample, xyz);
   int32_t *idx_buf = nullptr;
-  if (!idx_in) {
+  if (!idx_in && !fuse_query) {
     idx_buf = idx_out;
     if (!idx_buf) {
       const size_t need = align256(sizeof(int32_t) * (size_t)B * M * nsample);
@@ -512,11 +517,11 @@ extern "C" int b200pn2_sa_forward_planned(int B, int N, int M, int C, float radi
     B200_CUDA_OK(cudaMemsetAsync(unit_total, 0, sizeof(int), stream));
   }
   const int32_t *idx = idx_in;
-  if (!idx) {
+  if (!idx && !fuse_query) {
     const int rc = ball_query_launch(B, N, M, radius, nsample, new_xyz, xyz, idx_buf, stream, unit_list, unit_total);
     if (rc) return rc;
     idx = idx_buf;
-  } else {
+  } else if (idx) {
     if (idx_out && idx_out != idx_in)
       B200_CUDA_OK(cudaMemcpyAsync(idx_out, idx_in, sizeof(int32_t) * (size_t)B * M * nsample, cudaMemcpyDeviceToDevice,
                                    stream));
@@ -532,6 +537,7 @@ extern "C" int b200pn2_sa_forward_planned(int B, int N, int M, int C, float radi
     c.radius = radius; c.xyz = xyz; c.feat_pm = fpm; c.new_xyz = new_xyz; c.idx = idx; c.out = out; c.out_pm = out_pm;
     c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
     c.unit_list = unit_list; c.unit_total = unit_total;
+    c.query = fuse_query ? 1 : 0; c.idx_out = fuse_query ? idx_out : nullptr;
     return sa_tc_run(c, stream);
   }
 

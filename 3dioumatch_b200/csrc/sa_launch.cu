@@ -273,6 +273,9 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
     if (rc1) return rc1;
     p.feat_pm = P;
   }
+  p.query = (c.mode == 0 && c.query) ? 1 : 0;
+  p.radius2 = c.radius * c.radius;  // ball_query_gpu.cu:27, one fp32 multiply
+  p.idx_out = c.idx_out;
   p.units = 0;
   if (c.unit_list && c.unit_total) {
     p.units = 1; p.unit_list = c.unit_list; p.total_units = c.unit_total;

@@ -48,6 +48,12 @@ struct TcParams {
   const int *unit_list;    // unit u -> centre * 8 + first slot / 16
   const int *total_units;  // device scalar written by sa_units_kernel
   int units;               // 1: compacted mode
+  // fused ball query (QUERY kernels, sa_tcp.cu): idx == NULL, the producers stage the scene's coordinates in shared memory
+  // with one cp.async.bulk and find each centre's first-nsample ascending hits themselves (ball_query_gpu.cu:27-46);
+  // idx_out (optional) receives the lists
+  int query;
+  float radius2;
+  int32_t *idx_out;
   const int32_t *idx3;   // (B, M*ns, 3)
   const float *w3;       // (B, M*ns, 3)
   const float *rel3;     // (B, M*ns, 3) or NULL
@@ -119,7 +125,13 @@ struct TcCall {
   const void *plan = nullptr;      // packed by b200pn2_mlp_plan_build for exactly this stack, or NULL
   size_t plan_bytes = 0;
   int *unit_list = nullptr, *unit_total = nullptr;  // compacted tiles: built by the ball query (or sa_tcp_units_from_idx)
+  int query = 0;                 // mode 0 without idx: the kernel's producers run the ball query (see TcParams::query)
+  int32_t *idx_out = nullptr;    // optional (B, M, ns) destination of the fused query's lists
 };
+// can the persistent kernel's producers run the ball query of this stage themselves?  (uncompacted tiles, a scene's
+// coordinates fit the shared-memory staging buffer and can be copied with one 16-byte-granular cp.async.bulk)
+bool sa_tcp_query_fusable(int B, int N, int M, int nsample, const float *xyz);
+constexpr int TC_QUERY_MAX_N = 2048;
 bool sa_tc_supported(int C, int nsample, int use_xyz, int num_layers, const b200_mlp_layer *layers, const float *feat_pm);
 int sa_tc_run(const TcCall &c, cudaStream_t stream);
 

@@ -173,6 +173,58 @@ __device__ unsigned long long g_tcp_prof[48];
 #define TP_HLAP(cat)
 #endif
 
+// Fused ball query (QUERY kernels): one producer warp finds, for its CPW consecutive centres, the first `ns` points of
+// the staged scene (shared memory, [N][3]) inside the ball, in ascending point index -- the contract of
+// query_ball_point_kernel (ball_query_gpu.cu:27-46) and the predicate of ball_query.cu (same fp32 rounding sequence).
+// Four 32-point chunks are loaded per iteration (12 independent LDS) and tested against every centre; ballot + popc rank
+// the hits.  list[cw * ns + t] = t-th hit of centre cw, count[cw] = min(hits, ns).
+template <int CPW>
+__device__ __forceinline__ void query_scan(const float *__restrict__ s_xyz, int N, int ns, float radius2,
+                                           const float *__restrict__ centres, int live, int lane, int *list, int *count) {
+  float qx[CPW], qy[CPW], qz[CPW];
+  int cnt[CPW];
+#pragma unroll
+  for (int cw = 0; cw < CPW; ++cw) {
+    const bool on = cw < live;
+    qx[cw] = on ? centres[cw * 3 + 0] : 0.f;
+    qy[cw] = on ? centres[cw * 3 + 1] : 0.f;
+    qz[cw] = on ? centres[cw * 3 + 2] : 0.f;
+    cnt[cw] = on ? 0 : ns;  // nothing to find
+  }
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int k0 = 0; k0 < N; k0 += 128) {
+    bool full = true;
+#pragma unroll
+    for (int cw = 0; cw < CPW; ++cw) full = full && (cnt[cw] >= ns);
+    if (full) break;
+    float x[4], y[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 32 + lane;
+      const bool in = k < N;
+      x[u] = in ? s_xyz[k * 3 + 0] : 0.f;
+      y[u] = in ? s_xyz[k * 3 + 1] : 0.f;
+      z[u] = in ? s_xyz[k * 3 + 2] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u * 32 + lane;
+#pragma unroll
+      for (int cw = 0; cw < CPW; ++cw) {
+        const float d2 = sqdist3(qx[cw], qy[cw], qz[cw], x[u], y[u], z[u]);  // :36-37 (new - x)
+        const bool hit = k < N && d2 < radius2 && cnt[cw] < ns;             // :38 strict; :32 stop after ns hits
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt[cw] + __popc(mask & lt_mask);
+        if (hit && pos < ns) list[cw * ns + pos] = k;
+        cnt[cw] += __popc(mask);
+      }
+    }
+  }
+#pragma unroll
+  for (int cw = 0; cw < CPW; ++cw)
+    if (lane == 0) count[cw] = min(cnt[cw], ns);
+}
+
 // MODE: row source (0 ball-query lists, 1 three-neighbour blends, 2 plain row GEMM with row output); PRE: factorised first
 // layer (rows of P + xyz FMAs + ReLU in the producers).  Compile-time so that each variant's producer only carries its own
 // registers -- the gather is register-bound (a runtime-mode kernel with one more row source measured 20 % slower).
@@ -182,10 +234,17 @@ __device__ unsigned long long g_tcp_prof[48];
 // TRAIN: one layer of a training-mode stack (plain rows in, raw conv rows out): affine + ReLU of the previous layer's
 // batch-statistics BatchNorm applied to the input rows in the producers, per-tile column sums of the output (the next
 // BatchNorm's statistics) in the epilogue.
-template <int MODE, int PRE, int ROWOUT, int TRAIN = 0>
+// QUERY (mode 0, uncompacted tiles, nsample <= 32, N <= TC_QUERY_MAX_N): no neighbour lists come in.  The producer warps
+// stage the tile's scene coordinates in shared memory with ONE cp.async.bulk (mbarrier completion) and run the radius
+// search for their own rows' centres there -- first nsample hits in ascending point index, padded with the first hit,
+// zeros when the ball is empty (ball_query_gpu.cu:27-46) -- straight into the row gather: ball query and grouping are
+// one kernel, the (B, M, nsample) index tensor exists only if the caller asks for it (p.idx_out).
+template <int MODE, int PRE, int ROWOUT, int TRAIN = 0, int QUERY = 0>
 __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128-byte swizzle, by OFFSET from the __shared__ array: a round trip through uintptr_t
+  // loses the address space and turns every access below into a generic LD.E / ST.E with a descriptor R2UR pair
+  uint8_t *base = smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u);
   uint8_t *R1 = base;                                                        // layer-1 operand ring: TP_ASTAGES x 32 KB
   uint8_t *R2 = base + p.r1_bytes;                                           // weight ring: nslots x wslot_bytes
   float *s_scale = reinterpret_cast<float *>(R2 + p.nslots * p.wslot_bytes);  // [TC_MAXL][256]
@@ -194,6 +253,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
   float *s_wx = s_partial + 2 * 4 * 256;                                     // [3][128] scale1 * W1x (factorised layer 1)
   float *s_in = s_wx + 3 * 128;                                              // [4][256] input coefficients, [4][256] output (TRAIN)
   float *s_out = s_in + 4 * 256;
+  float *s_qxyz = s_out + 4 * 256;                                           // [N][3] staged scene coordinates (QUERY)
+  __shared__ uint64_t q_bar;
+  __shared__ int s_qlist[4][32], s_qcnt[4][4];                               // per producer warp: hit lists of its centres
 
   __shared__ uint64_t full_a[TP_ASTAGES], empty_a[TP_ASTAGES], full_w[TP_MAXSLOTS], empty_w[TP_MAXSLOTS];
   // accum_half is indexed by (accumulator region, half): a barrier advances once per TWO tiles, and the MMA warp may not
@@ -228,6 +290,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       tc::mbar_init(&tq_empty[s], TP_EPI + 128 + 1);  // epilogue + producer threads + one lane of the MMA warp
     }
     tc::mbar_init(&accum_full, 1);
+    tc::mbar_init(&q_bar, 1);
     tc::mbar_init(&x_ready, TP_EPI);
     tc::mbar_fence_init();
   }
@@ -431,6 +494,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
     const int g = row / ns;
     const int C = p.C;
     uint32_t sa = 0, pa = 0;
+    int q_scene = -1;        // QUERY: scene whose coordinates are staged in s_qxyz
+    uint32_t q_phase = 0;
     for (;;) {
       const int t = next_tile(true);
       if (t < 0) break;
@@ -462,9 +527,39 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       int src_idx = 0;
       float ctr[3] = {0.f, 0.f, 0.f};
       if (valid && MODE == 0) {
-        src_idx = p.idx[((size_t)b * p.M + m0 + gi) * ns + slot];
+        if (!QUERY) src_idx = p.idx[((size_t)b * p.M + m0 + gi) * ns + slot];
         const float *c = p.new_xyz + ((size_t)b * p.M + m0 + gi) * 3;
         ctr[0] = c[0]; ctr[1] = c[1]; ctr[2] = c[2];
+      }
+      if (QUERY && MODE == 0) {
+        // ---- fused ball query: this warp's rows are the nsample slots of 32 / ns consecutive centres -------------------
+        if (b != q_scene) {  // uniform over the producers: they walk the same tile sequence
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // every producer warp is done with the scene staged before
+          if (tid == TP_PROD0) {
+            tc::mbar_arrive_expect_tx(&q_bar, (uint32_t)p.N * 12u);
+            tc::bulk_g2s(s_qxyz, p.xyz + (size_t)b * p.N * 3, (uint32_t)p.N * 12u, &q_bar);
+          }
+          TPW(10, &q_bar, q_phase);
+          q_phase ^= 1u;
+          q_scene = b;
+        }
+        const int pw = warp - 8, cpw = 32 / ns;  // centres per warp: 4, 2 or 1
+        __syncwarp();  // the previous tile's lists have been read
+        const float *cbase = p.new_xyz + ((size_t)b * p.M + m0 + pw * cpw) * 3;
+        const int live = max(0, min(cpw, g_here - pw * cpw));  // warp-uniform
+        if (cpw == 2)
+          query_scan<2>(s_qxyz, p.N, ns, p.radius2, cbase, live, lane, s_qlist[pw], s_qcnt[pw]);
+        else if (cpw == 4)
+          query_scan<4>(s_qxyz, p.N, ns, p.radius2, cbase, live, lane, s_qlist[pw], s_qcnt[pw]);
+        else
+          query_scan<1>(s_qxyz, p.N, ns, p.radius2, cbase, live, lane, s_qlist[pw], s_qcnt[pw]);
+        __syncwarp();
+        if (valid) {
+          const int cw = lane / ns, have = s_qcnt[pw][cw];
+          // :39-46 slot t holds the t-th hit, the first hit fills the rest, an empty ball keeps the zero row
+          src_idx = slot < have ? s_qlist[pw][cw * ns + slot] : (have > 0 ? s_qlist[pw][cw * ns] : 0);
+          if (p.idx_out) p.idx_out[((size_t)b * p.M + m0 + gi) * ns + slot] = src_idx;
+        }
       }
       const float *frow = (valid && C > 0 && MODE == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
       if (valid && MODE == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * p.ld;
@@ -959,11 +1054,19 @@ int sa_tcp_units_from_idx(int B, int M, int nsample, const int32_t *idx, int *un
   return 0;
 }
 
-template <int MODE, int PRE, int ROWOUT, int TRAIN = 0>
+bool sa_tcp_query_fusable(int B, int N, int M, int nsample, const float *xyz) {
+  const char *e = getenv("B200_SA_TC_QUERY");  // read per call: the parity suite runs both ways in one process
+  if (e && atoi(e) == 0) return false;
+  // one 16-byte-granular bulk copy per scene (N * 12 bytes from a 16-byte-aligned base), rows of one warp = whole centres
+  return N >= 1 && N <= TC_QUERY_MAX_N && (N & 3) == 0 && ((((uintptr_t)xyz) & 15) == 0) && nsample >= 8 && nsample <= 32 &&
+         (32 % nsample) == 0 && (128 % nsample) == 0 && B >= 1 && M >= 1;
+}
+
+template <int MODE, int PRE, int ROWOUT, int TRAIN = 0, int QUERY = 0>
 static int launch_variant(const TcParams &p, int grid, size_t smem, cudaStream_t stream) {
   static DynSmemOptIn optin;  // one per kernel instantiation, per device inside
-  B200_CUDA_OK(optin.ensure(sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN>, smem));
-  sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN><<<grid, TP_THREADS, smem, stream>>>(p);
+  B200_CUDA_OK(optin.ensure(sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN, QUERY>, smem));
+  sa_tcp_kernel<MODE, PRE, ROWOUT, TRAIN, QUERY><<<grid, TP_THREADS, smem, stream>>>(p);
   B200_LAUNCH_OK("sa_tcp_kernel");
   return 0;
 }
@@ -985,12 +1088,14 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
   p.total_tiles = p.mode == 2 ? ceil_div(p.rows_total, TC_ROWS) : p.B * p.tiles_per_scene;
   p.tile_counter = tile_counter;
   p.final_shfl = 1;
+  if (p.query) B200_CHECK_ARG(p.mode == 0 && !p.units && !p.rowout && p.N <= TC_QUERY_MAX_N && (p.N & 3) == 0,
+                              "sa_forward(tc): fused ball query needs uncompacted tiles and N <= %d", TC_QUERY_MAX_N);
   const size_t fixed = 1024 + 2 * TC_MAXL * 256 * sizeof(float) + 2 * 4 * 256 * sizeof(float) + 3 * 128 * sizeof(float) +
-                       8 * 256 * sizeof(float);
+                       8 * 256 * sizeof(float) + (p.query ? (((size_t)p.N * 12 + 127) & ~(size_t)127) : 0);
   p.a_stages = (force_astages >= 2 && force_astages <= TP_ASTAGES) ? force_astages : 3;
   p.r1_bytes = p.a_stages * 2 * (int)TC_KB_BYTES;  // layer-1 operand ring only: hidden activations live in TMEM
   const size_t rest = fixed + (size_t)p.r1_bytes;
-  const size_t budget = 227 * 1024 - 512;          // dynamic + the kernel's static shared memory
+  const size_t budget = 227 * 1024 - 1024;         // dynamic + the kernel's static shared memory (<= 944 B)
   int slots = (int)((budget - rest) / (size_t)p.wslot_bytes);
   p.nslots = slots > TP_MAXSLOTS ? TP_MAXSLOTS : slots;
   if (force_slots >= 2 && force_slots < p.nslots) p.nslots = force_slots;
@@ -1003,6 +1108,10 @@ int sa_tcp_launch(TcParams &p, int *tile_counter, cudaStream_t stream) {
     return launch_variant<2, 0, 1, 1>(p, grid, smem, stream);
   }
   const int key = p.mode * 4 + (p.pre ? 2 : 0) + (p.rowout ? 1 : 0);
+  if (p.query) {
+    if (key == 0) return launch_variant<0, 0, 0, 0, 1>(p, grid, smem, stream);  // fused ball query -> gather -> MLP -> max
+    if (key == 2) return launch_variant<0, 1, 0, 0, 1>(p, grid, smem, stream);  //   with a factorised first layer
+  }
   switch (key) {
     case 0: return launch_variant<0, 0, 0>(p, grid, smem, stream);   // ball-query lists -> MLP -> max
     case 2: return launch_variant<0, 1, 0>(p, grid, smem, stream);   //   with a factorised first layer

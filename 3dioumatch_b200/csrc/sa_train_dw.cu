@@ -23,7 +23,9 @@ constexpr uint32_t DW_TILE_BYTES = 128 * 128;  // [128 channels][32 rows] fp32
 
 __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the 128-byte swizzle, by OFFSET from the __shared__ array: a round trip through uintptr_t
+  // loses the address space and turns every access below into a generic LD.E / ST.E with a descriptor R2UR pair
+  uint8_t *base = smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u);
   // stage s: A_hi | A_lo | B_hi | B_lo, 16 KB each
   __shared__ uint64_t full[DW_STAGES], empty[DW_STAGES], done;
   __shared__ uint32_t tmem_base_s;

@@ -36,6 +36,11 @@ unsigned long long b200_launch_count(void);
  * CTAs per scene), right when other kernels of a pipelined step share the GPU.  Results are identical (bit-exact) for
  * every shape.  Returns the previous policy; the B200_FPS_POLICY environment variable sets the initial value.      */
 int b200pn2_fps_set_policy(int policy);
+/* Tuning / test hook (no reference counterpart): force the FPS kernel generation (0 = fps_owner_kernel wherever it applies,
+ * 2 = fps_cluster_kernel of round 1; -1 = default: owner for cluster shapes, cluster kernel for one CTA) and the launch shape
+ * (cluster size, threads per CTA; 0 = cost model).  A shape that cannot hold the cloud in registers makes the next call
+ * fail with an argument error.  Results are bit-identical for every choice (tests/test_gpu_pointops.py).            */
+int b200pn2_fps_force_shape(int kernel, int cluster, int threads);
 
 /* furthest_point_sampling(points (B,N,3), nsamples) -> idx (B,m) int32
  * reference: sampling.cpp:70-91 + sampling_gpu.cu:74-234.

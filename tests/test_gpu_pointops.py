@@ -48,25 +48,35 @@ def test_fps_ball_query_three_nn_bit_exact(pkg, orc, name):
     assert np.array_equal(d2.cpu().numpy(), rd2), "three_nn dist2 differs"
 
 
-def test_fps_every_cluster_size_agrees(pkg, orc, monkeypatch):
-    """The register-resident kernel must give the same indices for every cluster size / thread count it can pick."""
-    import os
-    import subprocess
-    import sys
-    xyz = cases.cloud(7, 2, 9000, dup_frac=0.2, origin_frac=0.01)
-    ref = orc.furthest_point_sampling(xyz, 300)
-    np.save("/tmp/_fps_xyz.npy", xyz)
-    code = ("import importlib,sys,numpy as np,torch;sys.path.insert(0,%r);p=importlib.import_module('3dioumatch_b200');"
-            "p.install_dropin();import pointnet2._ext as e;x=torch.from_numpy(np.load('/tmp/_fps_xyz.npy')).cuda();"
-            "np.save('/tmp/_fps_out.npy',e.furthest_point_sampling(x,300).cpu().numpy())") % os.path.dirname(pkg.PKG_DIR)
-    for cs in (1, 2, 4, 8, 16):
-        for th in (32, 64, 128, 256, 512):
-            env = dict(os.environ, B200_FPS_CLUSTER=str(cs), B200_FPS_THREADS=str(th))
-            r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-            if r.returncode != 0 and "needs a scratch buffer" in (r.stderr + r.stdout):
-                continue  # this (cluster, threads) pair cannot hold the cloud in registers
-            assert r.returncode == 0, r.stderr[-2000:]
-            assert np.array_equal(np.load("/tmp/_fps_out.npy"), ref), "cluster=%d threads=%d" % (cs, th)
+def test_fps_every_cluster_size_agrees(pkg, orc):
+    """Every kernel generation (fps_owner_kernel with direct / redux record arg-max, fps_cluster_kernel) and every
+    (cluster size, threads per CTA) shape it can pick must give the reference's indices: duplicated points (exact ties,
+    also across warps and CTAs), points inside the origin-skip sphere, a cloud that leaves whole CTAs without candidates."""
+    import importlib
+    import pointnet2._ext as ext
+    cabi = importlib.import_module("3dioumatch_b200._cabi")
+    clouds = [(cases.cloud(7, 2, 9000, dup_frac=0.2, origin_frac=0.01), 300),
+              (cases.cloud(8, 3, 700, dup_frac=0.5, origin_frac=0.3), 700),       # npoint == N: the tail is all ties at 0
+              (np.concatenate([cases.cloud(9, 2, 40, dup_frac=0.3), np.zeros((2, 4000, 3), np.float32)], 1), 64)]
+    tried = 0
+    try:
+        for xyz, m in clouds:
+            ref = orc.furthest_point_sampling(xyz, m)
+            t = dev(xyz)
+            for kern in (-1, 0, 2):
+                for cs in (1, 2, 4, 8, 16):
+                    for th in (32, 64, 128, 256, 512):
+                        cabi.force_fps_shape(kern, cs, th)
+                        try:
+                            got = ext.furthest_point_sampling(t, m)
+                        except RuntimeError as e:
+                            assert "needs a scratch buffer" in str(e), str(e)  # this shape cannot hold the cloud in registers
+                            continue
+                        tried += 1
+                        assert np.array_equal(got.cpu().numpy(), ref), "kernel=%d cluster=%d threads=%d N=%d" % (kern, cs, th, xyz.shape[1])
+    finally:
+        cabi.force_fps_shape(-1, 0, 0)
+    assert tried >= 100
 
 
 def test_fps_scannet_shape_full_size(pkg, orc):

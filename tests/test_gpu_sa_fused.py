@@ -109,6 +109,43 @@ def test_sa_first_layer_factorised_and_not(orc, tr, pkg, monkeypatch, shape, fac
     run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 31 + M + 1, use_xyz=False)
 
 
+@pytest.mark.parametrize("shape", [
+    # (B, N, M, C, radius, ns, mlp): the levels whose ball query runs inside the fused kernel's producers
+    (8, 1024, 512, 256, 0.8, 16, [128, 128, 256]),    # SA3 at the bench shape
+    (8, 512, 256, 256, 1.2, 16, [128, 128, 256]),     # SA4
+    (8, 1024, 256, 256, 0.3, 16, [128, 128, 128]),    # vote aggregation: sparse balls, many short / empty lists
+    (3, 1024, 203, 256, 0.05, 16, [128, 128, 128]),   # radius so small that most balls hold only the centre itself
+    (2, 2048, 77, 8, 0.4, 8, [32, 64]),               # nsample 8: four centres per producer warp, no factorised layer
+    (2, 600, 150, 64, 0.5, 32, [64, 64]),             # nsample 32 (compaction off below): one centre per warp
+])
+def test_ball_query_fused_into_the_gather(orc, tr, pkg, monkeypatch, shape):
+    """Small levels: the tensor-core kernel's producers stage the scene in shared memory (one cp.async.bulk) and run the
+    radius search themselves (B200_SA_TC_QUERY, default on).  Neighbour lists bit-exact against the oracle when asked
+    for, features within 1e-5 of the fp32 reference, and bit-identical to the two-kernel path (separate ball query)."""
+    import pointnet2._ext as ext
+    B, N, M, C, r, ns, spec = shape
+    if ns == 32:
+        monkeypatch.setenv("B200_SA_TC_UNITS", "0")
+    run_case(orc, tr, B, N, M, C, r, ns, spec, seed=B * 13 + M, dup=0.03)
+    xyz = cases.cloud(B * 13 + M, B, N, dup_frac=0.03)
+    feats = np.random.default_rng(3).standard_normal((B, C, N)).astype(np.float32)
+    fps = orc.furthest_point_sampling(xyz, M)
+    new_xyz = np.take_along_axis(xyz, fps[:, :, None].astype(np.int64), 1)
+    trip = [(dev(w), dev(s), dev(h)) for w, s, h in tr.fold(cases.mlp_params(4, [C + 3] + list(spec)))]
+    args = (dev(xyz), dev(feats), dev(new_xyz), r, ns, trip)
+    cabi = __import__("importlib").import_module("3dioumatch_b200._cabi")
+    n0 = cabi.launch_count()
+    fused, _, _ = ext.sa_forward(*args, normalize_xyz=True)                    # no idx requested: none is written
+    n_fused = cabi.launch_count() - n0
+    fused_i, _, idx_f = ext.sa_forward(*args, normalize_xyz=True, want_idx=True)
+    monkeypatch.setenv("B200_SA_TC_QUERY", "0")
+    n0 = cabi.launch_count()
+    plain, _, idx_p = ext.sa_forward(*args, normalize_xyz=True, want_idx=True)
+    n_plain = cabi.launch_count() - n0
+    assert torch.equal(idx_f, idx_p) and torch.equal(fused, plain) and torch.equal(fused_i, plain)
+    assert n_fused == n_plain - 1                                              # the ball-query launch is gone
+
+
 def test_no_xyz_and_unnormalised(orc, tr, pkg):
     run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=5, use_xyz=False, normalize=False)
     run_case(orc, tr, 2, 900, 64, 12, 0.5, 16, [32, 32], seed=6, use_xyz=True, normalize=False)

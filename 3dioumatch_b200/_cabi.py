@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200pn2_fps_set_policy": (c_int, [c_int]),
     "b200pn2_fps_force_shape": (c_int, [c_int, c_int, c_int]),
+    "b200pn2_fps_set_prefix_speculation": (c_int, [c_int]),
     "b200pn2_furthest_point_sampling": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200pn2_gather_points_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -139,3 +140,9 @@ def force_fps_shape(kernel=-1, cluster=0, threads=0):
     """Tuning / test hook: kernel 0 fps_owner_kernel wherever it applies, 2 fps_cluster_kernel (round 1), -1 default;
     cluster / threads 0 = cost model (include/b200_pointnet2.h: b200pn2_fps_force_shape)."""
     lib().b200pn2_fps_force_shape(int(kernel), int(cluster), int(threads))
+
+
+def set_fps_prefix_speculation(mode):
+    """1 on, 0 off, -1 default (on): verify-then-skip for inputs already in furthest-point order (the hierarchical levels);
+    returns the previous mode (include/b200_pointnet2.h: b200pn2_fps_set_prefix_speculation)."""
+    return int(lib().b200pn2_fps_set_prefix_speculation(int(mode)))

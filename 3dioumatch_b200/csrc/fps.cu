@@ -101,7 +101,11 @@ __device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned remot
 // -- but the block scheduler spreads CTAs over free SMs first, so only a single CTA guarantees the sharing.
 template <int THREADS, int PPT, int MINB = 1, int GROUPS = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
-fps_cluster_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
+fps_cluster_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx,
+                   const int *__restrict__ redo) {
+  // prefix speculation (fps_prefix_check_kernel below) already produced this scene's indices: nothing to do.  The test is
+  // uniform over the cluster (one scene per cluster) and precedes every barrier.
+  if (GROUPS == 1 && redo && redo[blockIdx.y] == 0) return;
   constexpr int GT = THREADS / GROUPS;  // threads per scene in this CTA
   constexpr int NWARP = GT / 32;
   extern __shared__ float s_xyz_all[];  // [GROUPS][PPT][GT][3]
@@ -369,7 +373,9 @@ __device__ __forceinline__ float max_tree(const float (&t)[N]) {
 
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
-fps_owner_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx) {
+fps_owner_kernel(int B, int N, int m, int L, const float *__restrict__ xyz, int32_t *__restrict__ idx,
+                 const int *__restrict__ redo) {
+  if (redo && redo[blockIdx.y] == 0) return;  // see fps_cluster_kernel
   constexpr int NWARP = THREADS / 32;
   extern __shared__ float4 s_tab[];  // [PPT][THREADS] coordinates of this CTA's points: the owner's one LDS.128
   cg::cluster_group cluster = cg::this_cluster();
@@ -599,8 +605,147 @@ bool fps_pruned_wanted(int B, int N, int m);
 int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx, cudaStream_t stream);
 #endif
 
+// ---- prefix speculation: is the input already in furthest-point order? -------------------------------------------------
+// PointNet++ runs FPS hierarchically: level l+1 samples from the points level l selected, IN THE ORDER level l selected
+// them (pointnet2_modules.py:238-247, backbone_module.py:97-121; the proposal module's seed FPS the same,
+// proposal_module.py:98-104).  Furthest-point samples are nested: the j-th pick of level l maximises the min-distance
+// over the whole cloud, it is a member of the subset, so it also maximises it over the subset -- same operands, same
+// rounding sequence, same floats.  FPS of that subset therefore returns 0, 1, 2, ..., m-1 unless an exact tie or the
+// origin-skip rule intervenes (ties are ordered by the level's own thread ids, which differ between levels).
+// Instead of assuming it, three fully parallel kernels VERIFY it with the reference's exact semantics:
+//   fps_prefix_head_kernel   : the first 128 columns, self-contained -- refutes an ordinary cloud in microseconds;
+//   fps_prefix_values_kernel : V[j] = min-distance of point j to points 0..j-1 (what the reference's temp[j] holds when
+//                              step j picks), -1 for a point inside the skip sphere;
+//   fps_prefix_check_kernel  : every point k walks the columns j = 1..m-1 with its running min-distance and raises
+//                              redo[b] if at some step it would beat point j under (value desc, tie key asc).
+// No flag raised <=> at every step the reference's arg-max is point j  <=> idx = 0..m-1 exactly.  The serial kernel is
+// launched right behind with the same flag and returns immediately for verified scenes; a scene that fails (any input
+// not in furthest-point order fails at its first column, after a few microseconds) runs it in full.
+// m x N independent distance evaluations (2 M for 2048 -> 1024) instead of a 1023-step dependent chain.
+constexpr int FPS_PFX_THREADS = 128;
+constexpr int FPS_PFX_MAX_N = 4096;
+
+__global__ void __launch_bounds__(FPS_PFX_THREADS)
+fps_prefix_values_kernel(int N, int m, const float *__restrict__ xyz, float *__restrict__ V,
+                         const int *__restrict__ redo) {
+  __shared__ float s_p[FPS_PFX_THREADS * 3];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  if (redo[b]) return;  // already refuted by fps_prefix_head_kernel (uniform over the CTA)
+  const int j = blockIdx.x * FPS_PFX_THREADS + tid;
+  const float *pts = xyz + (size_t)b * N * 3;
+  float px = 0.f, py = 0.f, pz = 0.f, run = -1.0f;
+  if (j < m) {
+    px = pts[(size_t)j * 3]; py = pts[(size_t)j * 3 + 1]; pz = pts[(size_t)j * 3 + 2];
+    run = ((double)sq3(px, py, pz) <= 1e-3) ? -1.0f : 1e10f;  // sampling_gpu.cu:105-106, sampling.cpp:78-80
+  }
+  const int j_end = min(m, (blockIdx.x + 1) * FPS_PFX_THREADS);  // columns of this CTA need picks 0 .. j_end-2
+  for (int i0 = 0; i0 < j_end - 1; i0 += FPS_PFX_THREADS) {
+    __syncthreads();
+    const int n = min(FPS_PFX_THREADS, N - i0);
+    for (int e = tid; e < n * 3; e += FPS_PFX_THREADS) s_p[e] = pts[(size_t)i0 * 3 + e];
+    __syncthreads();
+    const int lim = min(n, j - i0);  // picks i < j only
+#pragma unroll 4
+    for (int i = 0; i < lim; ++i)
+      run = fminf(sqdist3(px, py, pz, s_p[i * 3], s_p[i * 3 + 1], s_p[i * 3 + 2]), run);  // :108-111 (x2 - x1)
+  }
+  if (j < m) V[(size_t)b * m + j] = run;
+}
+
+// First 128 columns only, self-contained (each CTA recomputes V[0..127] from the staged picks): an input that is NOT in
+// furthest-point order -- any ordinary cloud -- is refuted here within a few microseconds, and the two kernels below
+// return at once for that scene.
+__global__ void __launch_bounds__(FPS_PFX_THREADS)
+fps_prefix_head_kernel(int N, int m, int L, const float *__restrict__ xyz, int *__restrict__ redo) {
+  __shared__ float4 s_c[FPS_PFX_THREADS];
+  __shared__ unsigned s_key[FPS_PFX_THREADS];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int k = blockIdx.x * FPS_PFX_THREADS + tid;
+  const float *pts = xyz + (size_t)b * N * 3;
+  const unsigned bsmask = (1u << L) - 1u;
+  auto tie_key = [&](int q) -> unsigned {
+    const unsigned rev = L > 0 ? (__brev((unsigned)q & bsmask) >> (32 - L)) : 0u;
+    return (rev << 22) | ((unsigned)q >> L);
+  };
+  const int n = min(FPS_PFX_THREADS, m);
+  if (tid < n) {
+    s_c[tid] = make_float4(pts[(size_t)tid * 3], pts[(size_t)tid * 3 + 1], pts[(size_t)tid * 3 + 2], 0.f);
+    s_key[tid] = tie_key(tid);
+  }
+  __syncthreads();
+  if (tid < n) {  // V[tid]: min-distance of pick tid to the picks before it
+    const float4 me = s_c[tid];
+    float run = ((double)sq3(me.x, me.y, me.z) <= 1e-3) ? -1.0f : 1e10f;
+    for (int i = 0; i < tid; ++i) run = fminf(sqdist3(me.x, me.y, me.z, s_c[i].x, s_c[i].y, s_c[i].z), run);
+    s_c[tid].w = run;  // no hazard: the loop above reads x, y, z only; .w is read after the barrier below
+  }
+  __syncthreads();
+  if (k >= N) return;
+  const float px = pts[(size_t)k * 3], py = pts[(size_t)k * 3 + 1], pz = pts[(size_t)k * 3 + 2];
+  float run = ((double)sq3(px, py, pz) <= 1e-3) ? -1.0f : 1e10f;
+  const unsigned key_k = tie_key(k);
+  bool bad = false;
+#pragma unroll 4
+  for (int c = 0; c < n; ++c) {
+    const float4 s = s_c[c];
+    const bool beats = (run > s.w) || (run == s.w && key_k < s_key[c]);
+    bad = bad || (beats && c >= 1 && k != c);
+    run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);
+  }
+  if (bad) redo[b] = 1;
+}
+
+__global__ void __launch_bounds__(FPS_PFX_THREADS)
+fps_prefix_check_kernel(int N, int m, int L, const float *__restrict__ xyz, const float *__restrict__ V,
+                        int32_t *__restrict__ idx, int *__restrict__ redo) {
+  __shared__ float4 s_c[FPS_PFX_THREADS];  // pick j: x, y, z, V[j]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int k = blockIdx.x * FPS_PFX_THREADS + tid;
+  const float *pts = xyz + (size_t)b * N * 3;
+  const unsigned bsmask = (1u << L) - 1u;
+  auto tie_key = [&](int q) -> unsigned {
+    const unsigned rev = L > 0 ? (__brev((unsigned)q & bsmask) >> (32 - L)) : 0u;
+    return (rev << 22) | ((unsigned)q >> L);
+  };
+  float px = 0.f, py = 0.f, pz = 0.f, run = -1.0f;
+  const bool have = k < N;
+  if (have) {
+    px = pts[(size_t)k * 3]; py = pts[(size_t)k * 3 + 1]; pz = pts[(size_t)k * 3 + 2];
+    run = ((double)sq3(px, py, pz) <= 1e-3) ? -1.0f : 1e10f;
+  }
+  const unsigned key_k = tie_key(k);
+  if (k < m) idx[(size_t)b * m + k] = k;  // the speculated answer; the serial kernel overwrites it if the check fails
+  bool bad = false;
+  __shared__ unsigned s_key[FPS_PFX_THREADS];
+  __shared__ int s_stop;
+  for (int j0 = 0; j0 < m; j0 += FPS_PFX_THREADS) {
+    __syncthreads();  // the previous tile has been consumed
+    if (tid == 0) s_stop = *(volatile int *)&redo[b];  // someone already refuted the speculation: everybody leaves
+    const int j = j0 + tid;
+    if (j < m) {
+      s_c[tid] = make_float4(pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2], V[(size_t)b * m + j]);
+      s_key[tid] = tie_key(j);
+    }
+    __syncthreads();
+    if (s_stop) break;  // uniform
+    const int n = min(FPS_PFX_THREADS, m - j0);
+    if (have) {
+#pragma unroll 4
+      for (int c = 0; c < n; ++c) {
+        const float4 s = s_c[c];
+        const int jj = j0 + c;
+        // before pick jj is included, `run` is temp[k] as step jj sees it: does k beat the speculated pick jj?
+        const bool beats = (run > s.w) || (run == s.w && key_k < s_key[c]);
+        bad = bad || (beats && jj >= 1 && k != jj);
+        run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);
+      }
+    }
+    if (bad) redo[b] = 1;  // benign race: every writer stores 1
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
-typedef void (*fps_fn)(int, int, int, int, const float *, int32_t *);
+typedef void (*fps_fn)(int, int, int, int, const float *, int32_t *, const int *);
 
 template <int THREADS, int MINB = 1>
 static fps_fn pick_ppt(int ppt, int *ppt_out) {
@@ -710,12 +855,19 @@ extern "C" int b200pn2_fps_set_policy(int policy) {
 // tuning / test hook: force the kernel generation (0 fps_owner_kernel wherever it applies, 2 fps_cluster_kernel;
 // -1 = B200_FPS_KERNEL / default: owner for cluster shapes, fps_cluster_kernel for single-CTA shapes) and the launch
 // shape (0 = cost model).  Results are identical for every choice.
-static std::atomic<int> g_fps_force[3] = {{-1}, {0}, {0}};
+static std::atomic<int> g_fps_force[4] = {{-1}, {0}, {0}, {-1}};  // kernel, cluster, threads, prefix speculation
 extern "C" int b200pn2_fps_force_shape(int kernel, int cluster, int threads) {
   g_fps_force[0].store(kernel, std::memory_order_relaxed);
   g_fps_force[1].store(cluster, std::memory_order_relaxed);
   g_fps_force[2].store(threads, std::memory_order_relaxed);
   return 0;
+}
+// prefix speculation for clouds of at most 4096 points (see fps_prefix_check_kernel): 1 on, 0 off, -1 = B200_FPS_PREFIX /
+// default (on).  Results are identical either way.
+extern "C" int b200pn2_fps_set_prefix_speculation(int mode) {
+  const int prev = g_fps_force[3].load(std::memory_order_relaxed);
+  g_fps_force[3].store(mode, std::memory_order_relaxed);
+  return prev;
 }
 
 extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float *xyz, int32_t *idx, float *scratch,
@@ -826,6 +978,32 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
     return 0;
   }
 
+  // ---- prefix speculation for the small (hierarchical) levels ------------------------------------------------------
+  static int env_prefix = -1;
+  if (env_prefix < 0) {
+    const char *e = getenv("B200_FPS_PREFIX");
+    env_prefix = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const int f_prefix = g_fps_force[3].load(std::memory_order_relaxed);
+  const bool speculate = (f_prefix >= 0 ? f_prefix != 0 : env_prefix != 0) && N <= FPS_PFX_MAX_N && m >= 2 && m <= N &&
+                         best_fn != nullptr;
+  ScratchGuard pfx;
+  const int *redo = nullptr;
+  if (speculate) {
+    const size_t v_off = ((size_t)B * sizeof(int) + 255) & ~(size_t)255;
+    B200_CUDA_OK(pfx.alloc(v_off + (size_t)B * m * sizeof(float), stream));
+    int *redo_w = (int *)pfx.ptr;
+    float *V = (float *)((char *)pfx.ptr + v_off);
+    B200_CUDA_OK(cudaMemsetAsync(redo_w, 0, (size_t)B * sizeof(int), stream));
+    fps_prefix_head_kernel<<<dim3(ceil_div(N, FPS_PFX_THREADS), B), FPS_PFX_THREADS, 0, stream>>>(N, m, L, xyz, redo_w);
+    B200_LAUNCH_OK("fps_prefix_head_kernel");
+    fps_prefix_values_kernel<<<dim3(ceil_div(m, FPS_PFX_THREADS), B), FPS_PFX_THREADS, 0, stream>>>(N, m, xyz, V, redo_w);
+    B200_LAUNCH_OK("fps_prefix_values_kernel");
+    fps_prefix_check_kernel<<<dim3(ceil_div(N, FPS_PFX_THREADS), B), FPS_PFX_THREADS, 0, stream>>>(N, m, L, xyz, V, idx, redo_w);
+    B200_LAUNCH_OK("fps_prefix_check_kernel");
+    redo = redo_w;
+  }
+
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(best_cs, B, 1);
   cfg.blockDim = dim3(threads, 1, 1);
@@ -838,7 +1016,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, best_fn, B, N, m, L, xyz, idx));
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, best_fn, B, N, m, L, xyz, idx, redo));
   B200_LAUNCH_OK(best_own ? "fps_owner_kernel" : "fps_cluster_kernel");
   return 0;
 }

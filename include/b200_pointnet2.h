@@ -41,6 +41,13 @@ int b200pn2_fps_set_policy(int policy);
  * (cluster size, threads per CTA; 0 = cost model).  A shape that cannot hold the cloud in registers makes the next call
  * fail with an argument error.  Results are bit-identical for every choice (tests/test_gpu_pointops.py).            */
 int b200pn2_fps_force_shape(int kernel, int cluster, int threads);
+/* Prefix speculation of furthest_point_sampling for clouds of at most 4096 points (no reference counterpart).  The
+ * reference samples hierarchically from points that are already in furthest-point order (pointnet2_modules.py:238-247
+ * on the previous level's new_xyz), for which the answer is 0..m-1 unless a tie or the origin-skip rule intervenes; two
+ * parallel kernels verify exactly that with the reference's semantics (sampling_gpu.cu:105-114, 64-70) and the serial
+ * kernel behind them returns at once for verified scenes, runs in full for the others.  mode 1 on, 0 off, -1 default
+ * (on, or B200_FPS_PREFIX).  Returns the previous mode.  Results are bit-identical either way.                        */
+int b200pn2_fps_set_prefix_speculation(int mode);
 
 /* furthest_point_sampling(points (B,N,3), nsamples) -> idx (B,m) int32
  * reference: sampling.cpp:70-91 + sampling_gpu.cu:74-234.

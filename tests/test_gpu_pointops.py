@@ -79,6 +79,53 @@ def test_fps_every_cluster_size_agrees(pkg, orc):
     assert tried >= 100
 
 
+def test_fps_prefix_speculation(pkg, orc):
+    """Hierarchical levels: the input is the previous level's picks in pick order, for which FPS returns 0..m-1 unless a tie
+    or the origin-skip rule intervenes.  The verify-then-skip path (fps_prefix_values_kernel + fps_prefix_check_kernel,
+    b200pn2_fps_set_prefix_speculation) must give the oracle's indices when the speculation holds, when it fails for some
+    scenes of the batch only, and when it fails everywhere -- and the same indices as with speculation off."""
+    import importlib
+    import pointnet2._ext as ext
+    cabi = importlib.import_module("3dioumatch_b200._cabi")
+    rng = np.random.default_rng(11)
+    base = cases.scene_cloud(2, 4, 12000)[:, :, :3].copy()
+    lvl1 = orc.furthest_point_sampling(base, 2048)
+    ordered = np.take_along_axis(base, lvl1[:, :, None].astype(np.int64), 1)          # (4, 2048, 3) in furthest-point order
+    inputs = {"ordered": (ordered.copy(), 1024)}
+    mixed = ordered.copy()
+    mixed[1] = mixed[1][rng.permutation(2048)]                                          # scene 1: arbitrary order
+    mixed[2, 700] = mixed[2, 3]                                                         # scene 2: an exact duplicate -> a tie at the end of the chain
+    mixed[3, 5] = np.float32([0.01, -0.01, 0.005])                                      # scene 3: pick 5 falls inside the origin-skip sphere
+    inputs["mixed"] = (mixed, 1024)
+    inputs["random"] = (cases.cloud(12, 3, 1000, dup_frac=0.1, origin_frac=0.02), 500)
+    inputs["whole"] = (ordered[:2, :512].copy(), 512)                                   # m == N
+    lvl2 = orc.furthest_point_sampling(ordered, 1024)
+    assert np.array_equal(lvl2[0], np.arange(1024))                                     # the nesting property itself (oracle = reference semantics)
+    prev = cabi.set_fps_prefix_speculation(-1)
+    try:
+        for name, (xyz, m) in inputs.items():
+            ref = orc.furthest_point_sampling(xyz, m)
+            t = dev(xyz)
+            cabi.set_fps_prefix_speculation(1)
+            n0 = cabi.launch_count()
+            on = ext.furthest_point_sampling(t, m)
+            assert cabi.launch_count() - n0 == 4, "head + values + check + serial kernel"
+            cabi.set_fps_prefix_speculation(0)
+            n0 = cabi.launch_count()
+            off = ext.furthest_point_sampling(t, m)
+            assert cabi.launch_count() - n0 == 1
+            assert np.array_equal(on.cpu().numpy(), ref), name
+            assert torch.equal(on, off), name
+        # a cloud larger than the speculation limit is never speculated on
+        cabi.set_fps_prefix_speculation(1)
+        big = dev(base[:1, :6000].copy())
+        n0 = cabi.launch_count()
+        ext.furthest_point_sampling(big, 64)
+        assert cabi.launch_count() - n0 == 1
+    finally:
+        cabi.set_fps_prefix_speculation(prev)
+
+
 def test_fps_scannet_shape_full_size(pkg, orc):
     """BASELINE config: (B,N)=(8,40000) -> 2048 samples; one scene checked against the oracle, all scenes for
     size-independent properties (distinct indices, idx[0]=0, greedy max-min property on a sample of steps)."""

@@ -958,7 +958,7 @@ extern "C" int b200pn2_furthest_point_sampling(int B, int N, int m, const float 
                (cs > 8 ? 260.0 : 0.0);
       else
         iter = (ties ? 13.0 : 10.5) * ppt * warps_per_sched + 120.0 + (th > 32 ? 120.0 + 6.0 * (th / 32) : 0.0) +
-               (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 260.0 : 0.0);  // >8: non-portable size; also keeps half the SMs free
+               (cs > 1 ? 620.0 : 0.0) + (cs > 8 ? 60.0 : 0.0);  // >8: non-portable size (measured 16x128: 1160 cycles)
       // latency policy: serial chain length; throughput policy: SM-cycles per scene (cs CTAs hold an SM each)
       const double cost = throughput ? waves * iter * cs : waves * iter;
       if (cost < best_cost) {

@@ -193,7 +193,8 @@ def main(a, ROOT, ClockSampler, load_stack):
                                 "%d labeled + %d unlabeled scenes per GPU, N=%d, %d proposals" % (n_lab, n_unl, N, K)) if c5 else
                                ("configs[3]: SUN RGB-D-shaped pretrain.py step (forward_with_pred_jitter, get_labeled_loss, "
                                 "backward, Adam), %d scenes per GPU, N=%d, %d proposals" % (B, N, K)),
-                   "model": "models/votenet_iou_branch.py:VoteNet + models/loss_helper_%s.py (reference files, unmodified)" % (
+                   "model": "models/votenet_iou_branch.py:VoteNet + models/loss_helper_%s.py (reference files; --callers fast swaps "
+                            "in the module / loss-helper mirrors of SURVEY 8f n1-n3, see impl_options)" % (
                        "labeled/unlabeled" if c5 else "labeled"),
                    "scenes_per_gpu_per_step": B, "batchnorm": "training mode (batch statistics), per replica",
                    "parallelism": "scene-sharded data parallel, one flat-bucket gradient all-reduce per step"},

@@ -12,7 +12,7 @@ installed verbatim in baseline/_ref -- over one batch of B=8 synthetic ScanNet-s
 256 proposals, 64 padded GT slots).  Both arms run the SAME caller files; what differs is the operator stack under
 them: 3dioumatch_b200/dropin + libb200pc.so (this package) or the reference's pointnet2/_ext + iou3d_nms_cuda
 (oracle/_ref).  `--callers fast` additionally swaps in this package's mirrors of the voting / proposal / GridConv
-modules and of compute_iou_labels (same classes, same state-dict keys).
+modules, of compute_iou_labels and of the pseudo-label filter (same classes, same state-dict keys).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -646,6 +646,8 @@ def main():
                          "fps_policy": ("throughput" if (cabi and n_lanes > 1 and not os.environ.get("B200_FPS_POLICY"))
                                         else os.environ.get("B200_FPS_POLICY", "latency")) if cabi else None,
                          "block_diagonal_iou": bool(a.impl == "b200" and a.callers == "fast"),
+                         "fps_prefix_speculation": bool(cabi) and os.environ.get("B200_FPS_PREFIX", "1") != "0",
+                         "ball_query_fused_into_gather": bool(cabi) and os.environ.get("B200_SA_TC_QUERY", "1") != "0",
                          "stream": "legacy default stream, eager (the reference's IoU kernel launches there)" if a.impl == "reference"
                                    else "%d non-blocking streams" % len(runner.lanes)},
         "host_enqueue_ms_per_step": round(enqueue_ms, 4),

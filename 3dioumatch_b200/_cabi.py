@@ -67,6 +67,8 @@ PROTOTYPES = {
                                         c_void_p]),
     "b200pn2_row_mlp_forward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_int,
                                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200pn2_row_mlp_forward_cm": (c_int, [c_int, c_int, c_int, c_void_p, c_int, ctypes.POINTER(MlpLayer), c_int,
+                                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200pn2_transpose_cn": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "b200pn2_sa_train_saved_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(BnLayer), c_int]),
     "b200pn2_sa_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(BnLayer), c_int,

@@ -433,6 +433,25 @@ extern "C" int b200pn2_row_mlp_forward(int S, int R, int C, int ld, const float 
   return sa_tc_run(c, stream);
 }
 
+// The same stack on CHANNEL-MAJOR rows: x_cm (S, C, R) is what torch's conv stacks hold ((B, C, H, W) viewed (B, C, H*W));
+// the producers read it in place (one coalesced request per channel and warp), so no transpose pass precedes the GEMMs.
+extern "C" int b200pn2_row_mlp_forward_cm(int S, int R, int C, const float *x_cm, int num_layers,
+                                          const b200_mlp_layer *layers, int relu_last, float *out, float *out_pm,
+                                          const void *plan, size_t plan_bytes, b200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B200_CHECK_ARG(S >= 0 && R >= 0 && C > 0, "row_mlp_forward_cm: bad sizes");
+  B200_CHECK_ARG(x_cm && layers && (out || out_pm), "row_mlp_forward_cm: null pointer");
+  B200_CHECK_ARG((long long)S * R < (1ll << 30), "row_mlp_forward_cm: too many rows");
+  B200_CHECK_ARG(num_layers >= 1 && layers[0].cin == C, "row_mlp_forward_cm: layer 0 expects cin=%d", C);
+  if (S == 0 || R == 0) return 0;
+  TcCall c;
+  c.mode = 2; c.B = 1; c.N = S * R; c.M = S * R; c.C = C; c.ns = 32; c.use_xyz = 0;
+  c.feat_pm = x_cm; c.ld = C; c.cm_in = 1;
+  c.rowout = 1; c.final_relu = relu_last ? 1 : 0; c.rows_total = S * R; c.rows_per_scene = R;
+  c.out = out; c.out_pm = out_pm; c.num_layers = num_layers; c.layers = layers; c.plan = plan; c.plan_bytes = plan_bytes;
+  return sa_tc_run(c, stream);
+}
+
 extern "C" size_t b200pn2_sa_forward_workspace(int B, int N, int M, int C, int nsample, int have_features_pm,
                                                int have_idx) {
   size_t bytes = 0;

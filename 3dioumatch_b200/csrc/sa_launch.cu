@@ -241,6 +241,7 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
   p.out = c.out; p.out_pm = c.out_pm;
   p.rows_total = c.rows_total; p.rows_per_scene = c.rows_per_scene > 0 ? c.rows_per_scene : 1;
   p.ld = c.ld > 0 ? c.ld : c.C;
+  p.cm_in = (c.mode == 2 && c.cm_in) ? 1 : 0;
   p.in_scale = c.in_scale; p.in_shift = c.in_shift; p.stats = c.stats;
   p.train_in = c.train_in; p.train_out = c.train_out; p.pool_ns = c.pool_ns > 0 ? c.pool_ns : 1;
   p.g_rows = c.g_rows; p.gout_pm = c.gout_pm; p.dz_b = c.dz_b; p.dz_c = c.dz_c; p.arg_pm = c.arg_pm;
@@ -248,6 +249,7 @@ int sa_tc_run(const TcCall &c, cudaStream_t stream) {
   // 16-byte loads of whole 4-channel groups: aligned base and row stride; a ragged tail (C % 4) goes through scalar loads
   p.vec_gather = g.factor ? 1 : ((c.C >= 4 && (p.ld & 3) == 0 && (c.mode == 2 || (c.C & 3) == 0) &&
                                   ((((uintptr_t)c.feat_pm) & 15) == 0)) ? 1 : 0);
+  if (p.cm_in) p.vec_gather = 0;
   p.packed = plan;
   p.wslot_bytes = g.wslot_bytes;
   p.small_off = 128;

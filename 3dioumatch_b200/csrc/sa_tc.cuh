@@ -71,6 +71,10 @@ struct TcParams {
   const float *feat2_pm;
   int C2;
   int ld;  // mode 2: row stride of feat_pm in floats (>= C; rows padded to a multiple of 4 floats stay vector-loadable)
+  // mode 2, channel-major source: feat_pm is (S, C, rows_per_scene) -- the layout torch's conv stacks hand over
+  // (B, C, H, W); row r of scene s reads channel c at feat_pm[(s * C + c) * rows_per_scene + r].  The 32 lanes of a
+  // producer warp are 32 consecutive rows, so every channel is one coalesced 128-byte request: no transpose pass.
+  int cm_in;
   // training-mode layer passes (TRAIN kernels; sa_train.cu): input rows are the previous layer's raw conv output and
   // become relu(in_scale * z + in_shift) on their way into the operand ring (BatchNorm with batch statistics + ReLU,
   // pytorch_utils.py:42-61); the epilogue also emits per-tile column sums of the output and of its square,
@@ -111,6 +115,7 @@ struct TcCall {
   const float *feat2_pm = nullptr;
   int C2 = 0;
   int ld = 0;  // mode 2: row stride (0: C)
+  int cm_in = 0;  // mode 2: feat_pm is channel-major (S, C, rows_per_scene), see TcParams::cm_in
   const float *in_scale = nullptr, *in_shift = nullptr;  // training passes: affine + ReLU applied to the input rows
   float *stats = nullptr;                                 // training passes: per-tile column sums (see TcParams)
   int train_in = 0, train_out = 0, pool_ns = 1;           // backward passes (see TcParams)

@@ -563,6 +563,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
       }
       const float *frow = (valid && C > 0 && MODE == 0) ? p.feat_pm + ((size_t)b * p.N + src_idx) * C : nullptr;
       if (valid && MODE == 2) frow = p.feat_pm + ((size_t)t * TC_ROWS + row) * p.ld;
+      size_t cm_stride = 0;  // channel-major source (MODE 2): element (row, ch) = frow[ch * cm_stride]
+      if (MODE == 2 && !TRAIN && p.cm_in && valid) {
+        const size_t r = (size_t)t * TC_ROWS + row, sb = r / (size_t)p.rows_per_scene;
+        cm_stride = (size_t)p.rows_per_scene;
+        frow = p.feat_pm + sb * (size_t)C * cm_stride + (r - sb * cm_stride);
+      }
       // mode 1, second source: this row's own (skip) features follow the blended channels (PointnetFPModule's
       // torch.cat([interpolated, unknow_feats]), pointnet2_modules.py:413-418)
       const float *f2row = (MODE == 1 && valid && p.C2 > 0)
@@ -635,6 +641,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) sa_tcp_kernel(const TcParams p)
             v[c].y = in ? fmaf(c4.y, zv[c].y, fmaf(a4.y, g.y, b4.y)) : 0.f;
             v[c].z = in ? fmaf(c4.z, zv[c].z, fmaf(a4.z, g.z, b4.z)) : 0.f;
             v[c].w = in ? fmaf(c4.w, zv[c].w, fmaf(a4.w, g.w, b4.w)) : 0.f;
+          }
+          return;
+        }
+        if (MODE == 2 && !TRAIN && p.cm_in) {  // uniform: 32 coalesced scalar loads per k-block (lanes = consecutive rows)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = kb * 32 + c * 4;
+            v[c].x = (valid && ch + 0 < C) ? __ldg(frow + (size_t)(ch + 0) * cm_stride) : 0.f;
+            v[c].y = (valid && ch + 1 < C) ? __ldg(frow + (size_t)(ch + 1) * cm_stride) : 0.f;
+            v[c].z = (valid && ch + 2 < C) ? __ldg(frow + (size_t)(ch + 2) * cm_stride) : 0.f;
+            v[c].w = (valid && ch + 3 < C) ? __ldg(frow + (size_t)(ch + 3) * cm_stride) : 0.f;
           }
           return;
         }

@@ -346,6 +346,23 @@ def row_mlp_forward(x_pm, layers, relu_last=True, want_cm=True, want_pm=False, p
     return out, out_pm
 
 
+def row_mlp_forward_cm(x_cm, layers, relu_last=True, want_cm=True, want_pm=False, plan=None):
+    """The same stack on channel-major rows (b200pn2_row_mlp_forward_cm): x_cm (S,C,R) -- a (B,C,H,W) conv input viewed
+    (B,C,H*W) -- read in place, no transpose pass -> (out (S,cout,R), out_pm (S,R,cout))."""
+    _contig(x_cm, "x_cm"); _is_float(x_cm, "x_cm"); _cuda(x_cm, None)
+    S, C, R = x_cm.shape
+    arr, keep = _layer_array(layers)
+    cout = layers[-1][0].size(0)
+    dev = x_cm.device
+    out = torch.empty((S, cout, R), dtype=torch.float32, device=dev) if want_cm else None
+    out_pm = torch.empty((S, R, cout), dtype=torch.float32, device=dev) if want_pm else None
+    pp, pn = _plan_args(plan)
+    with torch.cuda.device(dev):
+        cabi.check(_L().b200pn2_row_mlp_forward_cm(S, R, C, _p(x_cm), len(layers), arr, int(bool(relu_last)), _p(out),
+                                                   _p(out_pm), pp, pn, stream_ptr()), "row_mlp_forward_cm")
+    return out, out_pm
+
+
 def split_row_groups(layers):
     """Cut a stack into runs one tensor-core launch can take: every layer of a run but its last is a hidden layer
     (width a multiple of 32, <= 128), the last may be up to 256 wide; at most 4 layers per run."""

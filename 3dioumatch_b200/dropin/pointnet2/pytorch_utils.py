@@ -174,14 +174,19 @@ class SharedMLP(nn.Sequential):
         if B * H * W == 0 or any(w.size(0) > 256 for w, _, _ in layers) or layers[0][0].size(1) != C:
             return None
         groups = _ext.split_row_groups(layers)
-        ld = (C + 3) // 4 * 4
-        rows = _ext.transpose_cn(x.contiguous().view(B, C, H * W), ld=ld)       # (B, H*W, ld)
-        chan = C
+        x_cm = x.contiguous().view(B, C, H * W)
+        rows, chan = None, C
         for gi, grp in enumerate(groups):
             last = gi == len(groups) - 1
             plan = self.b200_plan(grp, chan, False, row_output=True, plain_rows=True)
-            out_cm, out_pm = _ext.row_mlp_forward(rows, grp, relu_last=True, want_cm=last, want_pm=not last, plan=plan,
-                                                  channels=chan)
+            if gi == 0 and os.environ.get("B200_ROWS_CM", "1") != "0":
+                # the first run reads the channel-major conv input in place (no transpose pass)
+                out_cm, out_pm = _ext.row_mlp_forward_cm(x_cm, grp, relu_last=True, want_cm=last, want_pm=not last, plan=plan)
+            else:
+                if rows is None:
+                    rows = _ext.transpose_cn(x_cm, ld=(C + 3) // 4 * 4)          # (B, H*W, ld)
+                out_cm, out_pm = _ext.row_mlp_forward(rows, grp, relu_last=True, want_cm=last, want_pm=not last, plan=plan,
+                                                      channels=chan)
             rows, chan = out_pm, grp[-1][0].size(0)
         return out_cm.view(B, chan, H, W)
 

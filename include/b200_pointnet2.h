@@ -212,6 +212,11 @@ int b200pn2_fp_rows_forward(int B, int n, int m_known, int C2, int C1, const flo
 int b200pn2_row_mlp_forward(int S, int R, int C, int ld, const float *x_pm, int num_layers,
                             const b200_mlp_layer *layers, int relu_last, float *out, float *out_pm, const void *plan,
                             size_t plan_bytes, b200_stream_t stream);
+/* The same stack on channel-major input x_cm (S, C, R) -- the (B, C, H, W) tensor an eval-mode SharedMLP receives
+ * (pytorch_utils.py:14-39), read in place by the kernel's producers: no transpose pass.                             */
+int b200pn2_row_mlp_forward_cm(int S, int R, int C, const float *x_cm, int num_layers, const b200_mlp_layer *layers,
+                               int relu_last, float *out, float *out_pm, const void *plan, size_t plan_bytes,
+                               b200_stream_t stream);
 
 /* (B,C,N) channel-major -> (B,N,out_ld) point-major (the layout the fused kernels gather from); out_ld = 0: C,
  * otherwise >= C with zero-filled padding columns.                                                                  */

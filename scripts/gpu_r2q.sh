@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out/r2q; mkdir -p $O
+echo "== tests"; timeout 900 python -m pytest tests/test_gpu_tc_gemm.py tests/test_gpu_votenet_callers.py tests/test_gpu_sa_fused.py -q -x 2>&1 | grep -v Warn | tail -6 | tee $O/t.log
+run() { name=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 600 python bench.py --steps 300 --no-extras "$@" 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$name', d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])"; }
+run ref_cm1 B200_ROWS_CM=1 --
+run ref_cm0 B200_ROWS_CM=0 --
+run ref_cm1b B200_ROWS_CM=1 --
+echo "== step profile reference"; timeout 300 python scripts/step_profile.py reference 2>&1 | grep -v Warn | head -24 | cut -c1-150
+echo done

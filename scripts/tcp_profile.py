@@ -33,3 +33,38 @@ for (B, N, M, C, r, ns, spec) in cfgs:
     tiles = max(buf[21], 1)
     print("%s ns=%d: CTA0 ran %.1f tiles/launch; cycles per tile:" % (spec, ns, buf[21] / n))
     print("   " + "  ".join("%s %.0f" % (cats[c], buf[c] / tiles) for c in sorted(cats)))
+
+# ---- row MLPs (ROWOUT kernels): the GridConv mlp_before_iou of the unmodified reference callers (channel-major input),
+#      a per-point row GEMM (pass 1 of a factorised first layer) and a head-sized stack
+rows_cfgs = [("mlp_before_iou (8,259,16384) cm", 8, 16384, 259, [128, 128, 128], True),
+             ("mlp_before_iou (8,16384,260) pm", 8, 16384, 259, [128, 128, 128], False),
+             ("row GEMM 16384 x 128 -> 128", 1, 16384, 128, [128], False),
+             ("head 8192 rows 256 -> 256 -> 256", 8, 1024, 256, [128, 128], False)]
+for (name, S, R, C, spec, cm) in rows_cfgs:
+    g = torch.Generator(device="cuda").manual_seed(1)
+    layers, cin = [], C
+    for co in spec:
+        layers.append((torch.randn(co, cin, device="cuda", generator=g) / cin ** 0.5, torch.ones(co, device="cuda"),
+                       torch.zeros(co, device="cuda")))
+        cin = co
+    if cm:
+        x = torch.randn(S, C, R, device="cuda", generator=g)
+        call = lambda: ext.row_mlp_forward_cm(x, layers, relu_last=True, want_cm=True)
+    else:
+        ld = (C + 3) // 4 * 4
+        x = torch.randn(S, R, ld, device="cuda", generator=g)
+        call = lambda: ext.row_mlp_forward(x, layers, relu_last=True, want_cm=True, channels=C)
+    buf = (ctypes.c_ulonglong * 48)()
+    for _ in range(2):
+        call()
+    L.b200_debug_tcp_profile(buf)
+    n = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        call()
+    e1.record()
+    L.b200_debug_tcp_profile(buf)
+    tiles = max(buf[21], 1)
+    print("%s: %.3f ms/launch (profile build), CTA0 ran %.1f tiles/launch; cycles per tile:" % (name, e0.elapsed_time(e1) / n, buf[21] / n))
+    print("   " + "  ".join("%s %.0f" % (cats[c], buf[c] / tiles) for c in sorted(cats)))

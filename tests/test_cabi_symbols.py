@@ -54,3 +54,28 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
         assert "no CPU/PyTorch fallback" in str(e)
     else:
         raise AssertionError("expected RuntimeError")
+
+
+def test_shipped_library_holds_the_blackwell_native_instructions(pkg):
+    """The product library is sm_100a code built around the instructions DESIGN.md names, not a recompiled generic path:
+    tcgen05.mma / commit / ld / st (UTCHMMA, UTCBAR, LDTM, STTM), cp.async.bulk (UBLKCP), mbarrier (SYNCS), redux.sync
+    (CREDUX), cluster barriers and DSMEM st.async (UCGABAR_ARV, STAS), packed fp32 pairs (FFMA2).  SASS is read with
+    cuobjdump from the very file the GPU tests load; skipped where the CUDA toolkit is not installed."""
+    import shutil
+    import subprocess
+
+    import pytest
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not installed")
+    elf = subprocess.run([tool, "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf, elf[:200]
+    sass = subprocess.run([tool, "-sass", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic, at_least in (("UTCHMMA", 100), ("UTCBAR", 20), ("LDTM", 10), ("STTM", 5), ("UBLKCP", 5), ("SYNCS", 200),
+                               ("CREDUX", 50), ("UCGABAR_ARV", 10), ("STAS", 10), ("FFMA2", 100)):
+        n = len(re.findall(r"\b%s\b" % mnemonic, sass))
+        assert n >= at_least, "%s: %d occurrences" % (mnemonic, n)
+    # the tensor-core kernel variants the launcher can select, and both FPS generations, are all in the image
+    for kernel in ("sa_tcp_kernel", "fps_owner_kernel", "fps_cluster_kernel", "dw_tc_kernel", "bg_query_kernel",
+                   "pair_kernel", "nms_mask_kernel", "three_nn_kernel"):
+        assert kernel in sass, kernel

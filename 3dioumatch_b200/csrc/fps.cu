@@ -625,10 +625,40 @@ int fps_pruned_launch(int B, int N, int m, int L, const float *xyz, int32_t *idx
 constexpr int FPS_PFX_THREADS = 128;
 constexpr int FPS_PFX_MAX_N = 4096;
 
+// One tile of columns for one point k.  `run` is temp[k] as step j0 + c sees it BEFORE pick j0 + c is included.
+// Fast walk (branch-free, ~11 instructions per column): the speculated pick jj can only lose to k if run >= V[jj], which
+// in a cloud that is in furthest-point order happens for exact ties only -- so the walk records "some column had
+// run >= V" and nothing else.  A tile with such a column is replayed from the saved running value with the reference's
+// full rule (value desc, tie key asc, pick 0 fixed): sampling_gpu.cu:64-70,113-114.  s_c[c].w of column 0 is staged as
+// +inf (pick 0 is never contested), `own` = k - j0 is k's own column (its V equals `run` there by construction).
+__device__ __forceinline__ bool fps_prefix_walk(const float4 *__restrict__ s_c, const unsigned *__restrict__ s_key, int n,
+                                                int j0, int k, unsigned key_k, float px, float py, float pz, float &run) {
+  const float run0 = run;
+  const int own = k - j0;
+  int ge_seen = 0;
+#pragma unroll 8
+  for (int c = 0; c < n; ++c) {
+    const float4 s = s_c[c];
+    ge_seen |= (int)(run >= s.w) & (int)(c != own);
+    run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);  // :108-111
+  }
+  if (!ge_seen) return false;
+  bool bad = false;
+  float r = run0;
+  for (int c = 0; c < n; ++c) {  // rare
+    const float4 s = s_c[c];
+    const int jj = j0 + c;
+    const bool beats = (r > s.w) || (r == s.w && key_k < s_key[c]);
+    bad = bad || (beats && jj >= 1 && k != jj);
+    r = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), r);
+  }
+  return bad;
+}
+
 __global__ void __launch_bounds__(FPS_PFX_THREADS)
 fps_prefix_values_kernel(int N, int m, const float *__restrict__ xyz, float *__restrict__ V,
                          const int *__restrict__ redo) {
-  __shared__ float s_p[FPS_PFX_THREADS * 3];
+  __shared__ float4 s_p[2][FPS_PFX_THREADS];
   const int b = blockIdx.y, tid = threadIdx.x;
   if (redo[b]) return;  // already refuted by fps_prefix_head_kernel (uniform over the CTA)
   const int j = blockIdx.x * FPS_PFX_THREADS + tid;
@@ -639,15 +669,27 @@ fps_prefix_values_kernel(int N, int m, const float *__restrict__ xyz, float *__r
     run = ((double)sq3(px, py, pz) <= 1e-3) ? -1.0f : 1e10f;  // sampling_gpu.cu:105-106, sampling.cpp:78-80
   }
   const int j_end = min(m, (blockIdx.x + 1) * FPS_PFX_THREADS);  // columns of this CTA need picks 0 .. j_end-2
-  for (int i0 = 0; i0 < j_end - 1; i0 += FPS_PFX_THREADS) {
+  const int ntile = (j_end - 1 + FPS_PFX_THREADS - 1) / FPS_PFX_THREADS;
+  auto fetch = [&](int i0) -> float4 {  // pick i0 + tid (i0 + tid < j_end - 1 <= N for every pick that is read)
+    const int i = i0 + tid;
+    return i < N ? make_float4(pts[(size_t)i * 3], pts[(size_t)i * 3 + 1], pts[(size_t)i * 3 + 2], 0.f)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (ntile > 0) s_p[0][tid] = fetch(0);
+  __syncthreads();
+  for (int t = 0; t < ntile; ++t) {
+    const int i0 = t * FPS_PFX_THREADS;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t + 1 < ntile) nxt = fetch(i0 + FPS_PFX_THREADS);  // in flight under this tile's walk
+    const float4 *sp = s_p[t & 1];
+    const int lim = min(FPS_PFX_THREADS, j - i0);  // picks i < j only
+#pragma unroll 8
+    for (int i = 0; i < lim; ++i) {
+      const float4 s = sp[i];
+      run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);  // :108-111 (x2 - x1)
+    }
+    if (t + 1 < ntile) s_p[(t + 1) & 1][tid] = nxt;
     __syncthreads();
-    const int n = min(FPS_PFX_THREADS, N - i0);
-    for (int e = tid; e < n * 3; e += FPS_PFX_THREADS) s_p[e] = pts[(size_t)i0 * 3 + e];
-    __syncthreads();
-    const int lim = min(n, j - i0);  // picks i < j only
-#pragma unroll 4
-    for (int i = 0; i < lim; ++i)
-      run = fminf(sqdist3(px, py, pz, s_p[i * 3], s_p[i * 3 + 1], s_p[i * 3 + 2]), run);  // :108-111 (x2 - x1)
   }
   if (j < m) V[(size_t)b * m + j] = run;
 }
@@ -676,29 +718,26 @@ fps_prefix_head_kernel(int N, int m, int L, const float *__restrict__ xyz, int *
   if (tid < n) {  // V[tid]: min-distance of pick tid to the picks before it
     const float4 me = s_c[tid];
     float run = ((double)sq3(me.x, me.y, me.z) <= 1e-3) ? -1.0f : 1e10f;
-    for (int i = 0; i < tid; ++i) run = fminf(sqdist3(me.x, me.y, me.z, s_c[i].x, s_c[i].y, s_c[i].z), run);
-    s_c[tid].w = run;  // no hazard: the loop above reads x, y, z only; .w is read after the barrier below
+#pragma unroll 4
+    for (int i = 0; i < tid; ++i) {
+      const float4 s = s_c[i];
+      run = fminf(sqdist3(me.x, me.y, me.z, s.x, s.y, s.z), run);
+    }
+    // no hazard: the loop above reads x, y, z only; .w is read after the barrier below.  Pick 0 is never contested.
+    s_c[tid].w = tid == 0 ? __int_as_float(0x7f800000) : run;
   }
   __syncthreads();
   if (k >= N) return;
   const float px = pts[(size_t)k * 3], py = pts[(size_t)k * 3 + 1], pz = pts[(size_t)k * 3 + 2];
   float run = ((double)sq3(px, py, pz) <= 1e-3) ? -1.0f : 1e10f;
-  const unsigned key_k = tie_key(k);
-  bool bad = false;
-#pragma unroll 4
-  for (int c = 0; c < n; ++c) {
-    const float4 s = s_c[c];
-    const bool beats = (run > s.w) || (run == s.w && key_k < s_key[c]);
-    bad = bad || (beats && c >= 1 && k != c);
-    run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);
-  }
-  if (bad) redo[b] = 1;
+  if (fps_prefix_walk(s_c, s_key, n, 0, k, tie_key(k), px, py, pz, run)) redo[b] = 1;
 }
 
 __global__ void __launch_bounds__(FPS_PFX_THREADS)
 fps_prefix_check_kernel(int N, int m, int L, const float *__restrict__ xyz, const float *__restrict__ V,
                         int32_t *__restrict__ idx, int *__restrict__ redo) {
-  __shared__ float4 s_c[FPS_PFX_THREADS];  // pick j: x, y, z, V[j]
+  __shared__ float4 s_c[2][FPS_PFX_THREADS];  // pick j: x, y, z, V[j] (+inf for pick 0)
+  __shared__ unsigned s_key[2][FPS_PFX_THREADS];
   const int b = blockIdx.y, tid = threadIdx.x;
   const int k = blockIdx.x * FPS_PFX_THREADS + tid;
   const float *pts = xyz + (size_t)b * N * 3;
@@ -715,32 +754,34 @@ fps_prefix_check_kernel(int N, int m, int L, const float *__restrict__ xyz, cons
   }
   const unsigned key_k = tie_key(k);
   if (k < m) idx[(size_t)b * m + k] = k;  // the speculated answer; the serial kernel overwrites it if the check fails
-  bool bad = false;
-  __shared__ unsigned s_key[FPS_PFX_THREADS];
-  __shared__ int s_stop;
-  for (int j0 = 0; j0 < m; j0 += FPS_PFX_THREADS) {
-    __syncthreads();  // the previous tile has been consumed
-    if (tid == 0) s_stop = *(volatile int *)&redo[b];  // someone already refuted the speculation: everybody leaves
+  const float inf = __int_as_float(0x7f800000);
+  auto fetch = [&](int j0) -> float4 {  // column j0 + tid of the next tile: coordinates | V
     const int j = j0 + tid;
-    if (j < m) {
-      s_c[tid] = make_float4(pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2], V[(size_t)b * m + j]);
-      s_key[tid] = tie_key(j);
+    if (j >= m) return make_float4(0.f, 0.f, 0.f, inf);
+    return make_float4(pts[(size_t)j * 3], pts[(size_t)j * 3 + 1], pts[(size_t)j * 3 + 2],
+                       j == 0 ? inf : V[(size_t)b * m + j]);
+  };
+  s_c[0][tid] = fetch(0);
+  s_key[0][tid] = tie_key(tid);
+  int stop = *(volatile int *)&redo[b];  // someone already refuted the speculation: everybody leaves
+  int t = 0;
+  for (int j0 = 0; j0 < m; j0 += FPS_PFX_THREADS, ++t) {
+    if (__syncthreads_or(stop)) break;  // tile t staged (and tile t-1 consumed); uniform exit
+    const int nj0 = j0 + FPS_PFX_THREADS;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, inf);
+    if (nj0 < m) {  // next tile in flight under this tile's walk
+      nxt = fetch(nj0);
+      stop = *(volatile int *)&redo[b];
     }
-    __syncthreads();
-    if (s_stop) break;  // uniform
     const int n = min(FPS_PFX_THREADS, m - j0);
-    if (have) {
-#pragma unroll 4
-      for (int c = 0; c < n; ++c) {
-        const float4 s = s_c[c];
-        const int jj = j0 + c;
-        // before pick jj is included, `run` is temp[k] as step jj sees it: does k beat the speculated pick jj?
-        const bool beats = (run > s.w) || (run == s.w && key_k < s_key[c]);
-        bad = bad || (beats && jj >= 1 && k != jj);
-        run = fminf(sqdist3(px, py, pz, s.x, s.y, s.z), run);
-      }
+    if (have && fps_prefix_walk(s_c[t & 1], s_key[t & 1], n, j0, k, key_k, px, py, pz, run)) {
+      redo[b] = 1;  // benign race: every writer stores 1
+      stop = 1;
     }
-    if (bad) redo[b] = 1;  // benign race: every writer stores 1
+    if (nj0 < m) {
+      s_c[(t + 1) & 1][tid] = nxt;
+      s_key[(t + 1) & 1][tid] = tie_key(nj0 + tid);
+    }
   }
 }
 

@@ -324,21 +324,21 @@ def cpu_baseline(torch, points):
     for i, (m, r, nsm, spec) in enumerate(cfg):
         inds = orc.furthest_point_sampling(xyz, m)
         new_xyz = np.take_along_axis(xyz, inds[:, :, None].astype(np.int64), 1)
-        feat, _ = torch_ref.sa_forward(xyz, feat, new_xyz, r, nsm, synth.mlp_params(i, spec), normalize_xyz=True)
+        feat, _ = torch_ref.sa_forward(xyz, feat, new_xyz, r, nsm, synth.mlp_params(i, spec), normalize_xyz=True, exact=False)
         xyz = new_xyz
         levels.append((xyz, feat))
-    f = torch_ref.fp_forward(levels[2][0], levels[3][0], levels[2][1], levels[3][1], synth.mlp_params(10, [512, 256, 256]))
-    f = torch_ref.fp_forward(levels[1][0], levels[2][0], levels[1][1], f, synth.mlp_params(11, [512, 256, 256]))
+    f = torch_ref.fp_forward(levels[2][0], levels[3][0], levels[2][1], levels[3][1], synth.mlp_params(10, [512, 256, 256]), exact=False)
+    f = torch_ref.fp_forward(levels[1][0], levels[2][0], levels[1][1], f, synth.mlp_params(11, [512, 256, 256]), exact=False)
     seed_xyz = levels[1][0]
     inds = orc.furthest_point_sampling(seed_xyz, N_PROPOSAL)
     agg_xyz = np.take_along_axis(seed_xyz, inds[:, :, None].astype(np.int64), 1)
-    torch_ref.sa_forward(seed_xyz, f, agg_xyz, 0.3, 16, synth.mlp_params(12, [259, 128, 128, 128]), normalize_xyz=True)
+    torch_ref.sa_forward(seed_xyz, f, agg_xyz, 0.3, 16, synth.mlp_params(12, [259, 128, 128, 128]), normalize_xyz=True, exact=False)
     grid = (np.random.default_rng(0).random((1, N_PROPOSAL * 64, 3)) * [8, 8, 3] - [4, 4, 0]).astype(np.float32)
     d2, idx = orc.three_nn(grid, seed_xyz)
     w = np.full((1, N_PROPOSAL * 64, 3), 1 / 3, np.float32)
     interp = orc.three_interpolate(f, idx, w)
     x = torch.from_numpy(np.concatenate([np.zeros((1, 3, N_PROPOSAL * 64), np.float32), interp], 1)).view(1, 259, N_PROPOSAL, 64)
-    torch_ref.shared_mlp(x, synth.mlp_params(13, [259, 128, 128, 128]))
+    torch_ref.shared_mlp(x, synth.mlp_params(13, [259, 128, 128, 128]), exact=False)
     orc.boxes_iou3d(synth.boxes(0, N_PROPOSAL), synth.boxes(1, N_GT))
     dt = time.time() - t0
     return {"value": round(1.0 / dt, 4), "unit": "scenes/s", "cores": int(orc.num_threads()), "kind": "port",

@@ -97,7 +97,18 @@ def test_fps_prefix_speculation(pkg, orc):
     mixed[2, 700] = mixed[2, 3]                                                         # scene 2: an exact duplicate -> a tie at the end of the chain
     mixed[3, 5] = np.float32([0.01, -0.01, 0.005])                                      # scene 3: pick 5 falls inside the origin-skip sphere
     inputs["mixed"] = (mixed, 1024)
+    # exact ties between a speculated pick and a point that is never picked (k >= m): the tie key decides.  N = 2048 runs
+    # with 512-thread blocks in the reference (L = 9): key(10) = bitrev9(10) = 160; point 1500 (1500 % 512 = 476 ->
+    # bitrev9 = 119) wins the tie against pick 10 -> the speculation must be refuted; point 1535 (511 -> 511) loses it ->
+    # the speculation holds; pick 0 is never contested (scene 2: a copy of point 0)
+    ties = ordered.copy()
+    ties[0, 1500] = ties[0, 10]
+    ties[1, 1535] = ties[1, 10]
+    ties[2, 1300] = ties[2, 0]
+    ties[3, 1500] = ties[3, 1023]                                                       # a tie in the last column
+    inputs["ties"] = (ties, 1024)
     inputs["random"] = (cases.cloud(12, 3, 1000, dup_frac=0.1, origin_frac=0.02), 500)
+    inputs["ragged"] = (ordered[:3, :1000].copy(), 300)                                 # m, N not multiples of the 128-column tile
     inputs["whole"] = (ordered[:2, :512].copy(), 512)                                   # m == N
     lvl2 = orc.furthest_point_sampling(ordered, 1024)
     assert np.array_equal(lvl2[0], np.arange(1024))                                     # the nesting property itself (oracle = reference semantics)

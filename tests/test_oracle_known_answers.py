@@ -147,3 +147,33 @@ def test_nms_greedy(orc):
     assert orc.nms(b, 0.99).tolist() == [0, 1, 2, 3, 4]
     assert orc.nms(b, 0.5, normal=True).tolist() == [0, 2]
     assert orc.nms(np.zeros((0, 7), np.float32), 0.5).tolist() == []
+
+
+def test_module_restatement_float64_stack_agrees_with_the_literal_fp32_sequence(orc):
+    """oracle/torch_ref.py evaluates conv1x1 -> BN(eval) -> ReLU in float64 (rounded once) so that the checker does not
+    depend on the host's fp32 convolution.  It must be the same function as the literal fp32 torch sequence of the
+    reference (pytorch_utils.py:14-39,70-123): both run here on the SA and FP shapes of the parity tests and agree within
+    a fraction of the 1e-5 bar; max-pool / grouping / blending stay the fp32 ops they were."""
+    import numpy as np
+    import torch
+    import torch_ref as tr
+
+    import cases
+    rng = np.random.default_rng(3)
+    for spec, shape in (([7, 32, 64], (2, 7, 40, 16)), ([131, 128, 128, 256], (1, 131, 64, 32)), ([88, 48, 32], (2, 88, 512, 1))):
+        layers = cases.mlp_params(5, spec)
+        x = rng.standard_normal(shape).astype(np.float32)
+        exact = tr.shared_mlp(torch.from_numpy(x), layers).numpy()
+        literal = tr.shared_mlp(torch.from_numpy(x), layers, exact=False).numpy()
+        assert exact.dtype == np.float32 and exact.shape == literal.shape == (shape[0], spec[-1], shape[2], shape[3])
+        err = np.abs(exact - literal)
+        assert (err <= 0.5 * (1e-5 + 1e-5 * np.abs(exact))).all(), float(err.max())
+        assert np.array_equal(tr.shared_mlp(x, layers).numpy(), exact)          # arrays and tensors, deterministic
+    # the SA / FP wrappers pass the switch through
+    xyz = cases.cloud(4, 1, 300)
+    feats = rng.standard_normal((1, 4, 300)).astype(np.float32)
+    new_xyz = np.ascontiguousarray(xyz[:, :32])
+    layers = cases.mlp_params(6, [7, 32, 32])
+    a, ia = tr.sa_forward(xyz, feats, new_xyz, 0.3, 8, layers)
+    b, ib = tr.sa_forward(xyz, feats, new_xyz, 0.3, 8, layers, exact=False)
+    assert np.array_equal(ia, ib) and np.abs(a - b).max() <= 5e-6

@@ -133,3 +133,61 @@ def test_first_layer_factorisation_algebra():
     blend_p = (w3[:, :, None].astype(F) * P[i3]).sum(1)
     fused = np.maximum(blend_p + (rel.astype(F) @ wx.T), 0)
     assert np.abs(fused - direct).max() <= 1e-5 + 1e-5 * np.abs(direct).max()
+
+
+def _prefix_speculation_flag(xyz, m, bs, tile=None):
+    """numpy restatement of the verify-then-skip test of 3dioumatch_b200/csrc/fps.cu (fps_prefix_values_kernel +
+    fps_prefix_check_kernel): True = "the reference would not pick 0, 1, ..., m-1".  tile = None: the full rule in every
+    column; tile = T: the shipped two-stage form (a tile of T columns is examined with the full rule only if some column
+    had run >= V)."""
+    n = xyz.shape[0]
+    bits = bs.bit_length() - 1
+    key = np.asarray([(_bitrev(k % bs, bits) << 22) | (k >> bits) for k in range(n)], np.int64)
+    mag = _sqdist(xyz, np.zeros_like(xyz))
+    run = np.where(mag.astype(np.float64) <= 1e-3, F(-1), F(1e10)).astype(F)     # temp[k]; skipped points pinned at -1
+    R = np.empty((n, m), F)                                                       # R[k, j]: temp[k] as step j sees it
+    for j in range(m):
+        R[:, j] = run
+        run = np.minimum(_sqdist(xyz, xyz[j][None, :]), run).astype(F)
+    V = R[np.arange(m), np.arange(m)].copy()
+    V[0] = np.inf                                                                 # pick 0 is never contested
+    other = np.arange(n)[:, None] != np.arange(m)[None, :]
+    beats = ((R > V[None, :]) | ((R == V[None, :]) & (key[:, None] < key[None, :m]))) & other
+    beats[:, 0] = False
+    if tile is None:
+        return bool(beats.any())
+    ge = (R >= V[None, :]) & other
+    flag = False
+    for j0 in range(0, m, tile):
+        examined = ge[:, j0:j0 + tile].any(axis=1)                                # per point: replay this tile?
+        flag = flag or bool(beats[examined, j0:j0 + tile].any())
+    return flag
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 100_000), st.integers(4, 150), st.integers(2, 150), st.booleans(), st.sampled_from([0, 1, 2, 3]))
+def test_fps_prefix_speculation_is_exact(orc, seed, n, m, lattice, damage):
+    """The hierarchical FPS levels skip the serial kernel when three parallel kernels prove that the answer is
+    0, 1, ..., m-1.  The proof rule, restated in numpy, must say "holds" exactly when the oracle
+    (reference semantics: tie order by bit-reversed thread id, origin skip) returns 0..m-1 -- on clouds in furthest-point
+    order, with exact ties, duplicated points, points inside the skip sphere and arbitrary permutations -- and the
+    shipped two-stage form (cheap run >= V filter, full rule only for tiles that trip it) must decide identically."""
+    rng = np.random.default_rng(seed)
+    m = min(m, n)
+    xyz = (np.round(rng.random((n, 3)) * 4) if lattice else rng.random((n, 3)) * 2 - 1).astype(F)
+    order = orc.furthest_point_sampling(xyz[None], m)[0].astype(np.int64)
+    rest = np.setdiff1d(np.arange(n), order)
+    picks, first = np.unique(order, return_index=True)                          # a dead cloud repeats index 0
+    pts = np.concatenate([xyz[order[np.sort(first)]], xyz[rest]])[:n]
+    if pts.shape[0] < n:
+        pts = np.concatenate([pts, xyz[: n - pts.shape[0]]])
+    if damage == 1 and n > 3:                                                   # duplicate an early pick further back
+        pts[rng.integers(n // 2, n)] = pts[rng.integers(0, max(1, min(m, n // 2)))]
+    elif damage == 2:                                                           # a point inside the origin-skip sphere
+        pts[rng.integers(0, n)] = F([0.01, -0.01, 0.005])
+    elif damage == 3:                                                           # arbitrary order
+        pts = pts[rng.permutation(n)]
+    bs = orc.opt_n_threads(n)
+    holds = bool(np.array_equal(orc.furthest_point_sampling(pts[None], m)[0], np.arange(m)))
+    assert _prefix_speculation_flag(pts, m, bs) == (not holds)
+    assert _prefix_speculation_flag(pts, m, bs, tile=16) == (not holds)

@@ -79,3 +79,63 @@ def test_shipped_library_holds_the_blackwell_native_instructions(pkg):
     for kernel in ("sa_tcp_kernel", "fps_owner_kernel", "fps_cluster_kernel", "dw_tc_kernel", "bg_query_kernel",
                    "pair_kernel", "nms_mask_kernel", "three_nn_kernel"):
         assert kernel in sass, kernel
+
+
+def _header_prototypes():
+    """name -> (return type text, [parameter type texts]) parsed from include/*.h (comments stripped)."""
+    protos = {}
+    for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(b200\w*)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+            ret, name, params = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+            plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+            protos[name] = (ret, plist)
+    return protos
+
+
+def _kind(ctype_text):
+    """Coarse ABI class of a C parameter / return type."""
+    t = ctype_text.replace("const", " ").strip()
+    if "*" in t or "b200_stream_t" in t:
+        return "ptr"
+    if "size_t" in t or "unsigned long long" in t:
+        return "u64"            # both 8-byte unsigned on the LP64 targets this library is built for
+    if "double" in t:
+        return "double"
+    if "float" in t:
+        return "float"
+    if re.search(r"\bint\b|int32_t", t):
+        return "int"
+    raise AssertionError("unclassified C type: %r" % ctype_text)
+
+
+def test_ctypes_signatures_match_the_headers(pkg):
+    """Every prototype of include/*.h against the ctypes table: same number of parameters, and each parameter of the same
+    ABI class (int / float / 8-byte unsigned / pointer) in the same position -- an argument dropped or reordered on either side
+    would still load and then read garbage."""
+    import ctypes
+    cabi = pkg.cabi()
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(cabi.PROTOTYPES)
+
+    def ckind(t):
+        if t is ctypes.c_int:
+            return "int"
+        if t is ctypes.c_float:
+            return "float"
+        if t is ctypes.c_double:
+            return "double"
+        if t in (ctypes.c_size_t, ctypes.c_ulonglong):
+            return "u64"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        raise AssertionError("unclassified ctypes type: %r" % (t,))
+
+    for name, (ret, params) in sorted(protos.items()):
+        restype, argtypes = cabi.PROTOTYPES[name]
+        assert len(params) == len(argtypes), "%s: header has %d parameters, ctypes %d" % (name, len(params), len(argtypes))
+        got = [ckind(t) for t in argtypes]
+        want = [_kind(p) for p in params]
+        assert got == want, "%s: parameter classes differ\n  header %s\n  ctypes %s" % (name, want, got)
+        assert ckind(restype) == _kind(ret), "%s: return type %r vs %r" % (name, ret, restype)
